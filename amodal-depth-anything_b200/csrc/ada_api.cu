@@ -1,0 +1,1193 @@
+// libamodal_b200.so -- host side of the B200 forward pass of Amodal-Depth-Anything behind the C ABI of
+// include/amodal_b200.h: weight packing, workspace, kernel launch sequence. No torch types, no CPU fallback.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/amodal_b200.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "tma_host.h"
+
+namespace ada {
+
+static thread_local std::string g_last_error;
+
+struct AdaError : std::runtime_error {
+  int code;
+  AdaError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define ADA_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw AdaError(ADA_ECUDA, std::string(#expr) + " -> " + cudaGetErrorString(_e));               \
+  } while (0)
+#define ADA_REQUIRE(cond, msg)                                \
+  do {                                                        \
+    if (!(cond)) throw AdaError(ADA_EINVAL, std::string(msg)); \
+  } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline uint16_t f2bf(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn for finite values
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------ device context
+struct DeviceInfo {
+  int device = -1;
+  int sms = 0;
+  bool ok = false;
+  std::string why;
+};
+static DeviceInfo& device_info() {
+  static DeviceInfo di;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      di.why = std::string("no CUDA device: ") + cudaGetErrorString(e);
+      cudaGetLastError();
+      return di;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, dev);
+    if (p.major != 10) {
+      di.why = "device is sm_" + std::to_string(p.major) + std::to_string(p.minor) + ", this library is sm_100a only";
+      return di;
+    }
+    di.device = dev;
+    di.sms = p.multiProcessorCount;
+    di.ok = true;
+  }
+  return di;
+}
+static void require_device() {
+  DeviceInfo& di = device_info();
+  if (!di.ok) throw AdaError(ADA_ENODEVICE, di.why);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launcher
+template <int BN>
+static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int num_tiles,
+                           cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = std::min(num_tiles, device_info().sms);
+  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, g);
+  ADA_CHECK_CUDA(cudaGetLastError());
+}
+
+static int pick_bn(int N) {
+  // smallest padded N wins; ties go to the wider tile (fewer A re-reads, better smem operand bandwidth)
+  int best = 32, best_pad = round_up(N, 32);
+  const int cands[3] = {64, 128, 256};
+  for (int c : cands) {
+    const int pad = round_up(N, c);
+    if (pad <= best_pad + best_pad / 16) {  // allow ~6% padding for a wider tile
+      best = c;
+      best_pad = pad;
+    }
+  }
+  return best;
+}
+
+struct GemmLaunch {
+  const void* A = nullptr;   // linear: [M, K] pitch lda. conv: NHWC [batch, H, W, Cin]
+  const void* Bw = nullptr;  // [N, K] pitch ldb
+  int M = 0, N = 0, K = 0, lda = 0, ldb = 0;
+  int a_mode = A_LINEAR;
+  int batch = 0, H = 0, W = 0, Cin = 0;
+  GemmArgs args{};           // epilogue fields filled by caller
+  int force_bn = 0;
+};
+
+static int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
+
+static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
+  GemmArgs g = L.args;
+  g.M = L.M;
+  g.N = L.N;
+  g.K = L.K;
+  g.a_mode = L.a_mode;
+  int bn = L.force_bn ? L.force_bn : pick_bn(g.epi == EPI_SWIGLU ? std::max(L.N, 64) : L.N);
+  if (g.epi == EPI_TAIL) bn = 32;
+  if (g.epi == EPI_SWIGLU && bn < 64) bn = 64;
+  ADA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "bad BN");
+  ADA_REQUIRE(L.ldb % 8 == 0, "weight pitch must be a multiple of 8 elements");
+  CUtensorMap ta, tb;
+  int tiles_m;
+  if (L.a_mode == A_CONV3X3) {
+    ADA_REQUIRE(L.Cin % 8 == 0, "conv Cin must be a multiple of 8");
+    g.H = L.H;
+    g.W = L.W;
+    g.tiles_x = (L.W + kTileW - 1) / kTileW;
+    g.tiles_y = (L.H + kTileH - 1) / kTileH;
+    g.c_chunks = round_up(L.Cin, kBlockK) / kBlockK;
+    g.K = 9 * g.c_chunks * kBlockK;
+    uint64_t dims[4] = {static_cast<uint64_t>(L.Cin), static_cast<uint64_t>(L.W), static_cast<uint64_t>(L.H),
+                        static_cast<uint64_t>(L.batch)};
+    uint64_t str[3] = {static_cast<uint64_t>(L.Cin) * 2, static_cast<uint64_t>(L.W) * L.Cin * 2,
+                       static_cast<uint64_t>(L.H) * L.W * L.Cin * 2};
+    uint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+    ta = make_tmap_bf16(L.A, 4, dims, str, box);
+    tiles_m = L.batch * g.tiles_x * g.tiles_y;
+    ADA_REQUIRE(L.M == L.batch * L.H * L.W, "conv M mismatch");
+  } else {
+    ADA_REQUIRE(L.lda % 8 == 0, "A pitch must be a multiple of 8 elements");
+    ta = make_tmap_2d(L.A, static_cast<uint64_t>(L.K), static_cast<uint64_t>(L.M), static_cast<uint64_t>(L.lda), kBlockK,
+                      kBlockM);
+    tiles_m = (L.M + kBlockM - 1) / kBlockM;
+  }
+  tb = make_tmap_2d(L.Bw, static_cast<uint64_t>(g.K), static_cast<uint64_t>(L.N), static_cast<uint64_t>(L.ldb), kBlockK,
+                    static_cast<uint32_t>(bn));
+  const int tiles_n = (L.N + bn - 1) / bn;
+  const int num_tiles = tiles_m * tiles_n;
+  switch (bn) {
+    case 32: launch_gemm_bn<32>(ta, tb, g, num_tiles, st); break;
+    case 64: launch_gemm_bn<64>(ta, tb, g, num_tiles, st); break;
+    case 128: launch_gemm_bn<128>(ta, tb, g, num_tiles, st); break;
+    default: launch_gemm_bn<256>(ta, tb, g, num_tiles, st); break;
+  }
+  ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------ other launchers
+static void launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* out, int rows, int D,
+                             float eps, int n_tok, int drop_cls, cudaStream_t st) {
+  const int grid = (rows + 7) / 8;
+  switch (D / 128) {
+    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
+    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
+    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
+    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
+    default: throw AdaError(ADA_EINVAL, "layernorm: embed_dim must be 384/768/1024/1536");
+  }
+  ADA_REQUIRE(D % 128 == 0, "layernorm: D % 128");
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kAttSmemBytes));
+    attr_set = true;
+  }
+  const int D = heads * 64;
+  uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
+  uint32_t box[3] = {64, 128, 1};
+  CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
+  AttArgs a;
+  a.B = B;
+  a.N = N;
+  a.heads = heads;
+  a.D = D;
+  a.out = out;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
+  attention_tcgen05_kernel<<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, a);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+static void launch_channel_ln_relu(const __nv_bfloat16* in, const float* w, const float* b, __nv_bfloat16* out,
+                                   long long pixels, int C, float eps, cudaStream_t st) {
+  ADA_REQUIRE(C % 8 == 0 && C <= 1536, "channel LN: C % 8 == 0 and C <= 1536");
+  const int grid = static_cast<int>((pixels + 7) / 8);
+  if (C <= 512)
+    channel_ln_relu_kernel<2><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+  else
+    channel_ln_relu_kernel<6><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                            cudaStream_t st) {
+  ADA_REQUIRE(C % 8 == 0, "upsample: C % 8");
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  upsample_bilinear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, Hi, Wi, Ho, Wo, C);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+static void launch_patch_gather(const float* rgb, const float* const* guides, const int* guide_ch, int n_guides,
+                                __nv_bfloat16* out, int B, int H, int W, int Kpad, cudaStream_t st) {
+  ADA_REQUIRE(n_guides >= 0 && n_guides <= 3, "at most 3 guide tensors");
+  PatchSrc src{};
+  src.ptr[0] = rgb;
+  src.ch[0] = 3;
+  int C = 3;
+  for (int i = 0; i < n_guides; ++i) {
+    src.ptr[i + 1] = guides[i];
+    src.ch[i + 1] = guide_ch[i];
+    C += guide_ch[i];
+  }
+  src.n = n_guides + 1;
+  ADA_REQUIRE(C * 196 <= Kpad, "patch gather: Kpad too small");
+  const long long total = static_cast<long long>(B) * (H / 14) * C * 14 * (W / 14);
+  patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      src, out, B, C, H, W, Kpad, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+static void launch_im2col_s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, H, W, C, Ho, Wo);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// conv3x3 weight [Cout, Cin, 3, 3] (torch) -> [Cout, 9 * Cpad], K index = tap*Cpad + ci, zero padded channels.
+static std::vector<uint16_t> pack_conv3x3_host(const float* w, int Cout, int Cin) {
+  const int Cpad = round_up(Cin, kBlockK);
+  std::vector<uint16_t> o(static_cast<size_t>(Cout) * 9 * Cpad, 0);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < 9; ++t)
+        o[(static_cast<size_t>(co) * 9 + t) * Cpad + ci] = f2bf(w[(static_cast<size_t>(co) * Cin + ci) * 9 + t]);
+  return o;
+}
+// ConvTranspose2d weight [Cin, Cout, ks, ks] with stride == ks -> [(ky*ks+kx)*Cout + co, Cin]
+static std::vector<uint16_t> pack_convT_host(const float* w, int Cin, int Cout, int ks) {
+  std::vector<uint16_t> o(static_cast<size_t>(ks) * ks * Cout * Cin);
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int co = 0; co < Cout; ++co)
+      for (int kk = 0; kk < ks * ks; ++kk)
+        o[(static_cast<size_t>(kk) * Cout + co) * Cin + ci] = f2bf(w[(static_cast<size_t>(ci) * Cout + co) * ks * ks + kk]);
+  return o;
+}
+static std::vector<uint16_t> to_bf16_host(const float* w, size_t n) {
+  std::vector<uint16_t> o(n);
+  for (size_t i = 0; i < n; ++i) o[i] = f2bf(w[i]);
+  return o;
+}
+
+// Bicubic resampling of the position table, mirroring ATen upsample_bicubic2d (align_corners=False, A=-0.75) called
+// with an explicit scale_factor: src = (dst + 0.5) / scale_factor - 0.5, taps clamped to the border.
+static void cubic_coeffs(float t, float c[4]) {
+  const float A = -0.75f;
+  auto c1 = [&](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };
+  auto c2 = [&](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };
+  c[0] = c2(t + 1.f);
+  c[1] = c1(t);
+  c[2] = c1(1.f - t);
+  c[3] = c2(2.f - t);
+}
+static void interp_pos_host(const float* pos, int grid, int D, int gh, int gw, float offset, float* out) {
+  const double sf_h = static_cast<double>(gh + offset) / grid;  // python float math (dinov2.py:214-219)
+  const double sf_w = static_cast<double>(gw + offset) / grid;
+  const float rh = static_cast<float>(1.0 / sf_h), rw = static_cast<float>(1.0 / sf_w);
+  for (int oy = 0; oy < gh; ++oy) {
+    const float fy = rh * (oy + 0.5f) - 0.5f;
+    const int iy = static_cast<int>(floorf(fy));
+    float cy[4];
+    cubic_coeffs(fy - iy, cy);
+    for (int ox = 0; ox < gw; ++ox) {
+      const float fx = rw * (ox + 0.5f) - 0.5f;
+      const int ix = static_cast<int>(floorf(fx));
+      float cx[4];
+      cubic_coeffs(fx - ix, cx);
+      float* o = out + (static_cast<size_t>(oy) * gw + ox) * D;
+      for (int d = 0; d < D; ++d) o[d] = 0.f;
+      for (int a = 0; a < 4; ++a) {
+        const int yy = std::min(std::max(iy - 1 + a, 0), grid - 1);
+        float rowacc_w[4];
+        for (int b = 0; b < 4; ++b) rowacc_w[b] = cx[b] * cy[a];
+        for (int b = 0; b < 4; ++b) {
+          const int xx = std::min(std::max(ix - 1 + b, 0), grid - 1);
+          const float* p = pos + (static_cast<size_t>(yy) * grid + xx) * D;
+          const float wgt = rowacc_w[b];
+          for (int d = 0; d < D; ++d) o[d] += wgt * p[d];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ model
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  size_t numel() const { return data.size(); }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct BlockW {
+  float *ln1w, *ln1b, *ln2w, *ln2b, *bqkv, *bproj, *g1, *g2, *b1, *b2;
+  __nv_bfloat16 *wqkv, *wproj, *w1, *w2;
+};
+struct ConvW {
+  __nv_bfloat16* w = nullptr;
+  float* b = nullptr;
+  int cin = 0, cout = 0, ldw = 0;
+};
+struct RefineW {
+  ConvW rcu1c1, rcu1c2, rcu2c1, rcu2c2;
+  __nv_bfloat16* wout = nullptr;
+  float* bout = nullptr;
+};
+
+}  // namespace ada
+
+using namespace ada;
+
+struct ada_model {
+  ada_config cfg{};
+  std::unordered_map<std::string, HostTensor> host;  // raw fp32 state dict (released after finalize)
+  bool finalized = false;
+  bool capture = false;
+  std::vector<void*> owned;  // device allocations holding packed weights
+
+  // packed weights
+  int kpad = 0, cin_total = 0;
+  __nv_bfloat16* w_embed = nullptr;
+  std::vector<float> pos_host;      // [1 + grid*grid, D]
+  std::vector<float> cls_host;      // [D]
+  std::vector<float> embed_bias;    // [D] b_rgb + b_guide
+  std::vector<BlockW> blocks;
+  float *normw = nullptr, *normb = nullptr;
+  __nv_bfloat16* w_proj[4] = {};
+  float* b_proj[4] = {};
+  __nv_bfloat16* w_rs[4] = {};
+  float* b_rs[4] = {};
+  ConvW ip[4];
+  float *ipln_w[4] = {}, *ipln_b[4] = {};
+  ConvW rn[4];
+  RefineW ref[5];  // 1..4
+  ConvW oc1, oc2;
+  float* tail_aux = nullptr;  // 32 weights + 1 bias of output_conv2.2
+
+  // per-(H,W) position cache on device
+  struct PosCache {
+    float* posb = nullptr;     // [P, D] pos + embed bias
+    float* cls_pos = nullptr;  // [D]
+  };
+  std::map<std::pair<int, int>, PosCache> pos_cache;
+
+  // workspace
+  DevBuf arena;
+  int wsB = 0, wsH = 0, wsW = 0;
+  std::unordered_map<std::string, std::pair<void*, size_t>> named;  // intermediates (ptr, elements) + dtype by prefix
+  std::unordered_map<std::string, int> named_is_f32;
+  // buffers
+  float* x = nullptr;
+  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *a_embed = nullptr;
+  __nv_bfloat16* tap[4] = {};
+  float* tokens_dbg = nullptr;
+  __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *col4 = nullptr, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
+  __nv_bfloat16 *t1 = nullptr, *sum = nullptr, *sumr = nullptr, *r2 = nullptr, *ocb = nullptr, *path[5] = {},
+                *oc1b = nullptr, *up = nullptr;
+  int last_B = 0, last_H = 0, last_W = 0, last_launches = 0;
+
+  ~ada_model() {
+    for (void* p : owned) cudaFree(p);
+    if (arena.p) cudaFree(arena.p);
+    for (auto& kv : pos_cache) {
+      cudaFree(kv.second.posb);
+      cudaFree(kv.second.cls_pos);
+    }
+  }
+};
+
+namespace ada {
+
+template <typename T>
+static T* upload(ada_model* m, const void* src, size_t bytes) {
+  void* d = nullptr;
+  ADA_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  ADA_CHECK_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  m->owned.push_back(d);
+  return reinterpret_cast<T*>(d);
+}
+static const HostTensor& need(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
+  auto it = m->host.find(key);
+  if (it == m->host.end()) throw AdaError(ADA_ESTATE, "missing weight: " + key);
+  if (it->second.shape != shape) {
+    std::string s = "shape mismatch for " + key + ": got [";
+    for (auto v : it->second.shape) s += std::to_string(v) + ",";
+    s += "] expected [";
+    for (auto v : shape) s += std::to_string(v) + ",";
+    throw AdaError(ADA_EINVAL, s + "]");
+  }
+  return it->second;
+}
+static float* up_f32(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
+  const HostTensor& t = need(m, key, shape);
+  return upload<float>(m, t.data.data(), t.numel() * 4);
+}
+static __nv_bfloat16* up_bf16(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
+  const HostTensor& t = need(m, key, shape);
+  std::vector<uint16_t> h = to_bf16_host(t.data.data(), t.numel());
+  return upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+}
+static ConvW up_conv3x3(ada_model* m, const std::string& prefix, int cout, int cin, bool bias) {
+  const HostTensor& t = need(m, prefix + ".weight", {cout, cin, 3, 3});
+  std::vector<uint16_t> h = pack_conv3x3_host(t.data.data(), cout, cin);
+  ConvW c;
+  c.w = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+  c.cin = cin;
+  c.cout = cout;
+  c.ldw = 9 * round_up(cin, kBlockK);
+  c.b = bias ? up_f32(m, prefix + ".bias", {cout}) : nullptr;
+  return c;
+}
+
+static void finalize_model(ada_model* m) {
+  require_device();
+  const ada_config& c = m->cfg;
+  const int D = c.embed_dim, Cg = c.guide_channels, G = c.pos_grid;
+  const std::string pre = "pretrained.";
+  // ---- patch embed: fused (3+Cg)-channel weight, summed biases (dinov2.py:234-240)
+  m->cin_total = 3 + Cg;
+  m->kpad = round_up(m->cin_total * 196, kBlockK);
+  {
+    const HostTensor& wr = need(m, pre + "patch_embed.proj.weight", {D, 3, 14, 14});
+    const HostTensor& br = need(m, pre + "patch_embed.proj.bias", {D});
+    std::vector<uint16_t> w(static_cast<size_t>(D) * m->kpad, 0);
+    m->embed_bias.assign(br.data.begin(), br.data.end());
+    for (int d = 0; d < D; ++d)
+      for (int k = 0; k < 3 * 196; ++k) w[static_cast<size_t>(d) * m->kpad + k] = f2bf(wr.data[static_cast<size_t>(d) * 588 + k]);
+    if (Cg > 0) {
+      const HostTensor& wg = need(m, pre + "patch_embed_guidance.proj.weight", {D, Cg, 14, 14});
+      const HostTensor& bg = need(m, pre + "patch_embed_guidance.proj.bias", {D});
+      for (int d = 0; d < D; ++d) {
+        for (int k = 0; k < Cg * 196; ++k)
+          w[static_cast<size_t>(d) * m->kpad + 588 + k] = f2bf(wg.data[static_cast<size_t>(d) * Cg * 196 + k]);
+        m->embed_bias[d] += bg.data[d];
+      }
+    }
+    m->w_embed = upload<__nv_bfloat16>(m, w.data(), w.size() * 2);
+  }
+  m->pos_host = need(m, pre + "pos_embed", {1, 1 + G * G, D}).data;
+  m->cls_host = need(m, pre + "cls_token", {1, 1, D}).data;
+  need(m, pre + "mask_token", {1, D});  // dead weight, must exist for strict loading (dinov2.py:188)
+  // ---- blocks
+  m->blocks.resize(c.depth);
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string b = pre + "blocks." + std::to_string(i) + ".";
+    BlockW& w = m->blocks[i];
+    w.ln1w = up_f32(m, b + "norm1.weight", {D});
+    w.ln1b = up_f32(m, b + "norm1.bias", {D});
+    w.ln2w = up_f32(m, b + "norm2.weight", {D});
+    w.ln2b = up_f32(m, b + "norm2.bias", {D});
+    w.wqkv = up_bf16(m, b + "attn.qkv.weight", {3 * D, D});
+    w.bqkv = up_f32(m, b + "attn.qkv.bias", {3 * D});
+    w.wproj = up_bf16(m, b + "attn.proj.weight", {D, D});
+    w.bproj = up_f32(m, b + "attn.proj.bias", {D});
+    w.g1 = up_f32(m, b + "ls1.gamma", {D});
+    w.g2 = up_f32(m, b + "ls2.gamma", {D});
+    if (c.ffn_kind == 0) {
+      const int Hd = c.ffn_hidden;
+      w.w1 = up_bf16(m, b + "mlp.fc1.weight", {Hd, D});
+      w.b1 = up_f32(m, b + "mlp.fc1.bias", {Hd});
+      w.w2 = up_bf16(m, b + "mlp.fc2.weight", {D, Hd});
+      w.b2 = up_f32(m, b + "mlp.fc2.bias", {D});
+    } else {
+      // SwiGLU: interleave x1 / x2 rows in 32-wide chunks so one accumulator tile holds both halves (swiglu_ffn.py:30-32)
+      const int Hd = c.ffn_hidden;
+      const HostTensor& w12 = need(m, b + "mlp.w12.weight", {2 * Hd, D});
+      const HostTensor& b12 = need(m, b + "mlp.w12.bias", {2 * Hd});
+      std::vector<uint16_t> wi(static_cast<size_t>(2) * Hd * D);
+      std::vector<float> bi(2 * Hd);
+      for (int r = 0; r < 2 * Hd; ++r) {
+        const int chunk = r / 64, within = r % 64;
+        const int srow = (within < 32) ? chunk * 32 + within : Hd + chunk * 32 + (within - 32);
+        bi[r] = b12.data[srow];
+        for (int k = 0; k < D; ++k) wi[static_cast<size_t>(r) * D + k] = f2bf(w12.data[static_cast<size_t>(srow) * D + k]);
+      }
+      w.w1 = upload<__nv_bfloat16>(m, wi.data(), wi.size() * 2);
+      w.b1 = upload<float>(m, bi.data(), bi.size() * 4);
+      w.w2 = up_bf16(m, b + "mlp.w3.weight", {D, Hd});
+      w.b2 = up_f32(m, b + "mlp.w3.bias", {D});
+    }
+  }
+  m->normw = up_f32(m, pre + "norm.weight", {D});
+  m->normb = up_f32(m, pre + "norm.bias", {D});
+  // ---- DPT head
+  const std::string hd = "depth_head.";
+  const int F = c.features;
+  for (int i = 0; i < 4; ++i) {
+    const int Ci = c.out_channels[i];
+    const std::string si = std::to_string(i);
+    m->w_proj[i] = up_bf16(m, hd + "projects." + si + ".weight", {Ci, D, 1, 1});
+    m->b_proj[i] = up_f32(m, hd + "projects." + si + ".bias", {Ci});
+    if (i == 0 || i == 1) {
+      const int ks = (i == 0) ? 4 : 2;
+      const HostTensor& t = need(m, hd + "resize_layers." + si + ".weight", {Ci, Ci, ks, ks});
+      std::vector<uint16_t> h = pack_convT_host(t.data.data(), Ci, Ci, ks);
+      m->w_rs[i] = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+      m->b_rs[i] = up_f32(m, hd + "resize_layers." + si + ".bias", {Ci});
+    } else if (i == 3) {
+      const HostTensor& t = need(m, hd + "resize_layers.3.weight", {Ci, Ci, 3, 3});
+      ADA_REQUIRE(Ci % kBlockK == 0, "resize_layers.3 expects C % 64 == 0");
+      std::vector<uint16_t> h = pack_conv3x3_host(t.data.data(), Ci, Ci);
+      m->w_rs[i] = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+      m->b_rs[i] = up_f32(m, hd + "resize_layers.3.bias", {Ci});
+    }
+    m->ip[i] = up_conv3x3(m, hd + "input_projection." + si + ".0", Ci, Ci, true);
+    m->ipln_w[i] = up_f32(m, hd + "input_projection." + si + ".1.weight", {Ci});
+    m->ipln_b[i] = up_f32(m, hd + "input_projection." + si + ".1.bias", {Ci});
+    m->rn[i] = up_conv3x3(m, hd + "scratch.layer" + std::to_string(i + 1) + "_rn", F, Ci, false);
+  }
+  for (int k = 1; k <= 4; ++k) {
+    const std::string r = hd + "scratch.refinenet" + std::to_string(k) + ".";
+    RefineW& w = m->ref[k];
+    w.rcu1c1 = up_conv3x3(m, r + "resConfUnit1.conv1", F, F, true);  // dead for refinenet4 (blocks.py:131-133) but loaded
+    w.rcu1c2 = up_conv3x3(m, r + "resConfUnit1.conv2", F, F, true);
+    w.rcu2c1 = up_conv3x3(m, r + "resConfUnit2.conv1", F, F, true);
+    w.rcu2c2 = up_conv3x3(m, r + "resConfUnit2.conv2", F, F, true);
+    w.wout = up_bf16(m, r + "out_conv.weight", {F, F, 1, 1});
+    w.bout = up_f32(m, r + "out_conv.bias", {F});
+  }
+  m->oc1 = up_conv3x3(m, hd + "scratch.output_conv1", F / 2, F, true);
+  m->oc2 = up_conv3x3(m, hd + "scratch.output_conv2.0", 32, F / 2, true);
+  {
+    const HostTensor& w2 = need(m, hd + "scratch.output_conv2.2.weight", {1, 32, 1, 1});
+    const HostTensor& b2 = need(m, hd + "scratch.output_conv2.2.bias", {1});
+    float aux[33];
+    for (int i = 0; i < 32; ++i) aux[i] = w2.data[i];
+    aux[32] = b2.data[0];
+    m->tail_aux = upload<float>(m, aux, sizeof(aux));
+  }
+  m->host.clear();
+  m->finalized = true;
+}
+
+static ada_model::PosCache& get_pos(ada_model* m, int gh, int gw) {
+  auto key = std::make_pair(gh, gw);
+  auto it = m->pos_cache.find(key);
+  if (it != m->pos_cache.end()) return it->second;
+  const int D = m->cfg.embed_dim, G = m->cfg.pos_grid;
+  std::vector<float> pp(static_cast<size_t>(gh) * gw * D);
+  if (gh == G && gw == G) {  // dinov2.py:203-204: table used as is
+    std::copy(m->pos_host.begin() + D, m->pos_host.end(), pp.begin());
+  } else {
+    interp_pos_host(m->pos_host.data() + D, G, D, gh, gw, m->cfg.interpolate_offset, pp.data());
+  }
+  for (size_t p = 0; p < static_cast<size_t>(gh) * gw; ++p)
+    for (int d = 0; d < D; ++d) pp[p * D + d] += m->embed_bias[d];
+  std::vector<float> cp(D);
+  for (int d = 0; d < D; ++d) cp[d] = m->cls_host[d] + m->pos_host[d];
+  ada_model::PosCache pc;
+  ADA_CHECK_CUDA(cudaMalloc(&pc.posb, pp.size() * 4));
+  ADA_CHECK_CUDA(cudaMemcpy(pc.posb, pp.data(), pp.size() * 4, cudaMemcpyHostToDevice));
+  ADA_CHECK_CUDA(cudaMalloc(&pc.cls_pos, D * 4));
+  ADA_CHECK_CUDA(cudaMemcpy(pc.cls_pos, cp.data(), D * 4, cudaMemcpyHostToDevice));
+  return m->pos_cache[key] = pc;
+}
+
+// ---- workspace: one arena, bump-allocated, rebuilt when a larger (B,H,W) arrives
+struct Bump {
+  char* base;
+  size_t off = 0;
+  bool dry;
+  template <typename T>
+  T* take(size_t elems) {
+    off = (off + 1023) & ~static_cast<size_t>(1023);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += elems * sizeof(T);
+    return p;
+  }
+};
+
+static int down2(int h) { return (h - 1) / 2 + 1; }
+
+static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* base) {
+  const ada_config& c = m->cfg;
+  const int D = c.embed_dim, F = c.features;
+  const int gh = H / 14, gw = W / 14, P = gh * gw, N = P + 1;
+  const size_t M = static_cast<size_t>(B) * N, BP = static_cast<size_t>(B) * P;
+  Bump b{base, 0, dry};
+  m->named.clear();
+  m->named_is_f32.clear();
+  auto reg = [&](const std::string& n, void* p, size_t elems, int f32) {
+    m->named[n] = {p, elems};
+    m->named_is_f32[n] = f32;
+  };
+  m->x = b.take<float>(M * D);
+  m->xn = b.take<__nv_bfloat16>(M * D);
+  m->qkv = b.take<__nv_bfloat16>(M * 3 * D);
+  m->att = b.take<__nv_bfloat16>(M * D);
+  m->hbuf = b.take<__nv_bfloat16>(M * c.ffn_hidden);
+  m->a_embed = b.take<__nv_bfloat16>(BP * m->kpad);
+  m->tokens_dbg = b.take<float>(M * D);
+  reg("tokens", m->tokens_dbg, M * D, 1);
+  for (int i = 0; i < 4; ++i) {
+    m->tap[i] = b.take<__nv_bfloat16>(BP * D);
+    reg("tap" + std::to_string(i), m->tap[i], BP * D, 0);
+  }
+  const int sh[4] = {gh * 4, gh * 2, gh, down2(gh)}, sw[4] = {gw * 4, gw * 2, gw, down2(gw)};
+  size_t maxpix = 0;
+  for (int i = 0; i < 4; ++i) {
+    const size_t pix = static_cast<size_t>(B) * sh[i] * sw[i];
+    const int Ci = c.out_channels[i];
+    maxpix = std::max(maxpix, pix);
+    m->proj[i] = b.take<__nv_bfloat16>(BP * Ci);
+    m->rs[i] = (i == 2) ? m->proj[i] : b.take<__nv_bfloat16>(pix * Ci);
+    m->ipb[i] = b.take<__nv_bfloat16>(pix * Ci);
+    m->rnb[i] = b.take<__nv_bfloat16>(pix * F);
+    m->rnr[i] = b.take<__nv_bfloat16>(pix * F);
+    reg("layer" + std::to_string(i + 1) + "_rn", m->rnb[i], pix * F, 0);
+    reg("layer" + std::to_string(i + 1), m->ipb[i], pix * Ci, 0);
+  }
+  m->col4 = b.take<__nv_bfloat16>(static_cast<size_t>(B) * sh[3] * sw[3] * 9 * c.out_channels[3]);
+  m->t1 = b.take<__nv_bfloat16>(maxpix * F);
+  m->sum = b.take<__nv_bfloat16>(maxpix * F);
+  m->sumr = b.take<__nv_bfloat16>(maxpix * F);
+  m->r2 = b.take<__nv_bfloat16>(maxpix * F);
+  m->ocb = b.take<__nv_bfloat16>(maxpix * F);
+  // path_k lives at the resolution of level k-1 (path_1: 2x level 1)
+  const int ph[5] = {0, sh[0] * 2, sh[0], sh[1], sh[2]}, pw[5] = {0, sw[0] * 2, sw[0], sw[1], sw[2]};
+  for (int k = 1; k <= 4; ++k) {
+    const size_t pix = static_cast<size_t>(B) * ph[k] * pw[k];
+    m->path[k] = b.take<__nv_bfloat16>(pix * F);
+    reg("path_" + std::to_string(k), m->path[k], pix * F, 0);
+  }
+  m->oc1b = b.take<__nv_bfloat16>(static_cast<size_t>(B) * ph[1] * pw[1] * (F / 2));
+  m->up = b.take<__nv_bfloat16>(static_cast<size_t>(B) * H * W * (F / 2));
+  return b.off + 1024;
+}
+
+static void ensure_workspace(ada_model* m, int B, int H, int W) {
+  if (B == m->wsB && H == m->wsH && W == m->wsW) return;
+  const size_t need_bytes = plan_workspace(m, B, H, W, true, nullptr);
+  if (need_bytes > m->arena.bytes) {
+    if (m->arena.p) {
+      ADA_CHECK_CUDA(cudaDeviceSynchronize());
+      ADA_CHECK_CUDA(cudaFree(m->arena.p));
+      m->arena.p = nullptr;
+      m->arena.bytes = 0;
+    }
+    ADA_CHECK_CUDA(cudaMalloc(&m->arena.p, need_bytes));
+    m->arena.bytes = need_bytes;
+  }
+  plan_workspace(m, B, H, W, false, static_cast<char*>(m->arena.p));
+  // zero the K padding of the patch matrix once (the gather never writes it)
+  ADA_CHECK_CUDA(cudaMemset(m->a_embed, 0, static_cast<size_t>(B) * (H / 14) * (W / 14) * m->kpad * 2));
+  ADA_CHECK_CUDA(cudaDeviceSynchronize());
+  m->wsB = B;
+  m->wsH = H;
+  m->wsW = W;
+}
+
+// conv3x3 (pad 1, stride 1) over NHWC bf16 through the implicit-GEMM path
+static void conv3x3(const __nv_bfloat16* in, int B, int H, int W, const ConvW& cw, int act, const __nv_bfloat16* r1,
+                    const __nv_bfloat16* r2, __nv_bfloat16* out, __nv_bfloat16* out_relu, cudaStream_t st) {
+  GemmLaunch L;
+  L.A = in;
+  L.Bw = cw.w;
+  L.M = B * H * W;
+  L.N = cw.cout;
+  L.ldb = cw.ldw;
+  L.a_mode = A_CONV3X3;
+  L.batch = B;
+  L.H = H;
+  L.W = W;
+  L.Cin = cw.cin;
+  L.args.epi = EPI_BF16;
+  L.args.act = act;
+  L.args.bias = cw.b;
+  L.args.resid1 = r1;
+  L.args.resid2 = r2;
+  L.args.out_bf16 = out;
+  L.args.out_relu = out_relu;
+  L.args.ldo = cw.cout;
+  launch_gemm(L, st);
+}
+
+static void linear(const __nv_bfloat16* A, int M, int K, int lda, const __nv_bfloat16* Wt, int N, int ldb,
+                   const GemmArgs& epi, cudaStream_t st) {
+  GemmLaunch L;
+  L.A = A;
+  L.Bw = Wt;
+  L.M = M;
+  L.N = N;
+  L.K = K;
+  L.lda = lda;
+  L.ldb = ldb;
+  L.args = epi;
+  launch_gemm(L, st);
+}
+
+static void forward_impl(ada_model* m, const float* rgb, const float* const* guides, const int* guide_ch, int n_guides,
+                         float* out, int B, int H, int W, cudaStream_t st) {
+  require_device();
+  if (!m->finalized) throw AdaError(ADA_ESTATE, "ada_forward before ada_finalize");
+  ADA_REQUIRE(B > 0 && H > 0 && W > 0, "B, H, W must be positive");
+  ADA_REQUIRE(H % 14 == 0, "Input image height is not a multiple of patch height 14");
+  ADA_REQUIRE(W % 14 == 0, "Input image width is not a multiple of patch width 14");
+  int cg = 0;
+  for (int i = 0; i < n_guides; ++i) cg += guide_ch[i];
+  ADA_REQUIRE(cg == m->cfg.guide_channels, "guide channels do not match guide_type");
+  const ada_config& c = m->cfg;
+  const int D = c.embed_dim, F = c.features, heads = c.num_heads;
+  const int gh = H / 14, gw = W / 14, P = gh * gw, N = P + 1;
+  const int M = B * N, BP = B * P;
+  ensure_workspace(m, B, H, W);
+  ada_model::PosCache& pc = get_pos(m, gh, gw);
+  g_launches = 0;
+
+  // ---- tokens: patch gather -> embed GEMM (+bias +pos) ; cls rows     (dav2.py:65-76, dinov2.py:232-246)
+  launch_patch_gather(rgb, guides, guide_ch, n_guides, m->a_embed, B, H, W, m->kpad, st);
+  cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(pc.cls_pos, m->x, B, N, D);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+  {
+    GemmArgs e{};
+    e.epi = EPI_EMBED;
+    e.aux = pc.posb;
+    e.out_f32 = m->x;
+    e.ldo = D;
+    e.P = P;
+    linear(m->a_embed, BP, m->kpad, m->kpad, m->w_embed, D, m->kpad, e, st);
+  }
+  if (m->capture)
+    ADA_CHECK_CUDA(cudaMemcpyAsync(m->tokens_dbg, m->x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- encoder blocks (block.py:82-107 eval branch)
+  int tap_i = 0;
+  for (int i = 0; i < c.depth; ++i) {
+    const BlockW& w = m->blocks[i];
+    launch_layernorm(m->x, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, st);
+    {
+      GemmArgs e{};
+      e.epi = EPI_BF16;
+      e.bias = w.bqkv;
+      e.out_bf16 = m->qkv;
+      e.ldo = 3 * D;
+      linear(m->xn, M, D, D, w.wqkv, 3 * D, D, e, st);
+    }
+    launch_attention(m->qkv, m->att, B, N, heads, st);
+    {
+      GemmArgs e{};
+      e.epi = EPI_RESID_F32;
+      e.bias = w.bproj;
+      e.gamma = w.g1;
+      e.resid_f32 = m->x;
+      e.out_f32 = m->x;
+      e.ldo = D;
+      linear(m->att, M, D, D, w.wproj, D, D, e, st);
+    }
+    launch_layernorm(m->x, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, st);
+    const int Hd = c.ffn_hidden;
+    {
+      GemmArgs e{};
+      e.bias = w.b1;
+      e.out_bf16 = m->hbuf;
+      e.ldo = Hd;
+      if (c.ffn_kind == 0) {
+        e.epi = EPI_BF16;
+        e.act = ACT_GELU;
+        linear(m->xn, M, D, D, w.w1, Hd, D, e, st);
+      } else {
+        e.epi = EPI_SWIGLU;
+        linear(m->xn, M, D, D, w.w1, 2 * Hd, D, e, st);
+      }
+    }
+    {
+      GemmArgs e{};
+      e.epi = EPI_RESID_F32;
+      e.bias = w.b2;
+      e.gamma = w.g2;
+      e.resid_f32 = m->x;
+      e.out_f32 = m->x;
+      e.ldo = D;
+      linear(m->hbuf, M, Hd, Hd, w.w2, D, Hd, e, st);
+    }
+    if (tap_i < 4 && i == c.taps[tap_i]) {  // shared final norm, cls dropped, NHWC patch map (dinov2.py:337-340)
+      launch_layernorm(m->x, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, st);
+      ++tap_i;
+    }
+  }
+  if (tap_i != 4) throw AdaError(ADA_EINVAL, "taps must be increasing block indices < depth");
+
+  // ---- DPT head (dpt.py:161-197)
+  const int sh[4] = {gh * 4, gh * 2, gh, down2(gh)}, sw[4] = {gw * 4, gw * 2, gw, down2(gw)};
+  for (int i = 0; i < 4; ++i) {
+    const int Ci = c.out_channels[i];
+    {  // projects[i]: 1x1 conv D -> C_i (dpt.py:172)
+      GemmArgs e{};
+      e.epi = EPI_BF16;
+      e.bias = m->b_proj[i];
+      e.out_bf16 = m->proj[i];
+      e.ldo = Ci;
+      linear(m->tap[i], BP, D, D, m->w_proj[i], Ci, D, e, st);
+    }
+    if (i == 0 || i == 1) {  // ConvTranspose k == s (dpt.py:89-100): GEMM + pixel-shuffle scatter
+      const int ks = (i == 0) ? 4 : 2;
+      GemmArgs e{};
+      e.epi = EPI_CONVT;
+      e.bias = m->b_rs[i];
+      e.out_bf16 = m->rs[i];
+      e.H = gh;
+      e.W = gw;
+      e.ks = ks;
+      e.cout = Ci;
+      linear(m->proj[i], BP, Ci, Ci, m->w_rs[i], ks * ks * Ci, Ci, e, st);
+    } else if (i == 3) {  // conv 3x3 stride 2 (dpt.py:102-107): gather + GEMM
+      launch_im2col_s2(m->proj[3], m->col4, B, gh, gw, Ci, st);
+      GemmArgs e{};
+      e.epi = EPI_BF16;
+      e.bias = m->b_rs[3];
+      e.out_bf16 = m->rs[3];
+      e.ldo = Ci;
+      linear(m->col4, B * sh[3] * sw[3], 9 * Ci, 9 * Ci, m->w_rs[3], Ci, 9 * Ci, e, st);
+    }
+    // input_projection[i]: conv3x3 + channel LN + ReLU (dpt.py:153-159,178-179)
+    conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
+    launch_channel_ln_relu(m->ipb[i], m->ipln_w[i], m->ipln_b[i], m->ipb[i], static_cast<long long>(B) * sh[i] * sw[i],
+                           Ci, 1e-6f, st);
+    // layer{i}_rn: conv3x3 C_i -> F, no bias (blocks.py:20-24); keep x and relu(x) for the residual units
+    conv3x3(m->ipb[i], B, sh[i], sw[i], m->rn[i], ACT_NONE, nullptr, nullptr, m->rnb[i], m->rnr[i], st);
+  }
+  // refinenet4..1 (blocks.py:123-148). out_conv (1x1) commutes with the bilinear resize, so it runs at low resolution.
+  const int ph[5] = {0, sh[0] * 2, sh[0], sh[1], sh[2]}, pw[5] = {0, sw[0] * 2, sw[0], sw[1], sw[2]};
+  for (int k = 4; k >= 1; --k) {
+    const int lv = k - 1;  // pyramid level of this block's input
+    const int hh = sh[lv], ww = sw[lv];
+    const RefineW& rw = m->ref[k];
+    const __nv_bfloat16 *xin, *xin_relu;
+    if (k == 4) {
+      xin = m->rnb[3];
+      xin_relu = m->rnr[3];
+    } else {
+      // output = path_{k+1} + RCU1(layer_k_rn)
+      conv3x3(m->rnr[lv], B, hh, ww, rw.rcu1c1, ACT_RELU, nullptr, nullptr, m->t1, nullptr, st);
+      conv3x3(m->t1, B, hh, ww, rw.rcu1c2, ACT_NONE, m->rnb[lv], m->path[k + 1], m->sum, m->sumr, st);
+      xin = m->sum;
+      xin_relu = m->sumr;
+    }
+    conv3x3(xin_relu, B, hh, ww, rw.rcu2c1, ACT_RELU, nullptr, nullptr, m->t1, nullptr, st);
+    conv3x3(m->t1, B, hh, ww, rw.rcu2c2, ACT_NONE, xin, nullptr, m->r2, nullptr, st);
+    {
+      GemmArgs e{};
+      e.epi = EPI_BF16;
+      e.bias = rw.bout;
+      e.out_bf16 = m->ocb;
+      e.ldo = F;
+      linear(m->r2, B * hh * ww, F, F, rw.wout, F, F, e, st);
+    }
+    launch_upsample(m->ocb, m->path[k], B, hh, ww, ph[k], pw[k], F, st);
+  }
+  // output_conv1 -> bilinear to (H, W) -> output_conv2 (conv3x3 + ReLU + 1x1 + Sigmoid) (dpt.py:193-195)
+  conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st);
+  launch_upsample(m->oc1b, m->up, B, ph[1], pw[1], H, W, F / 2, st);
+  {
+    GemmLaunch L;
+    L.A = m->up;
+    L.Bw = m->oc2.w;
+    L.M = B * H * W;
+    L.N = 32;
+    L.ldb = m->oc2.ldw;
+    L.a_mode = A_CONV3X3;
+    L.batch = B;
+    L.H = H;
+    L.W = W;
+    L.Cin = F / 2;
+    L.args.epi = EPI_TAIL;
+    L.args.bias = m->oc2.b;
+    L.args.aux = m->tail_aux;
+    L.args.out_f32 = out;
+    L.args.sigmoid = c.sigmoid;
+    launch_gemm(L, st);
+  }
+  m->last_B = B;
+  m->last_H = H;
+  m->last_W = W;
+  m->last_launches = g_launches;
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* in, float* out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return ADA_OK;
+  } catch (const AdaError& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return ADA_EINVAL;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return ADA_EINVAL;
+  }
+}
+
+}  // namespace ada
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* ada_last_error(void) { return g_last_error.c_str(); }
+
+int ada_device_error(uint32_t out[4]) {
+  return guarded([&] { ADA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_dev_error, 16)); });
+}
+
+int ada_create(const ada_config* cfg, ada_handle* out) {
+  return guarded([&] {
+    ADA_REQUIRE(cfg && out, "null argument");
+    ADA_REQUIRE(cfg->embed_dim == cfg->num_heads * 64, "head_dim must be 64");
+    ADA_REQUIRE(cfg->embed_dim % 128 == 0, "embed_dim % 128");
+    ADA_REQUIRE(cfg->features % 16 == 0 && cfg->features >= 64, "features must be a multiple of 16, >= 64");
+    ADA_REQUIRE(cfg->guide_channels >= 0 && cfg->guide_channels <= 5, "guide_channels in [0,5]");
+    for (int i = 0; i < 4; ++i) ADA_REQUIRE(cfg->out_channels[i] % 8 == 0, "out_channels % 8");
+    ada_model* m = new ada_model();
+    m->cfg = *cfg;
+    *out = m;
+  });
+}
+
+int ada_set_weight(ada_handle h, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+  return guarded([&] {
+    ADA_REQUIRE(h && key && data && shape && ndim >= 0 && ndim <= 8, "bad argument");
+    if (h->finalized) throw AdaError(ADA_ESTATE, "ada_set_weight after ada_finalize");
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+      t.shape.push_back(shape[i]);
+      n *= static_cast<size_t>(shape[i]);
+    }
+    t.data.resize(n);
+    cudaPointerAttributes attr;
+    bool on_device = false;
+    if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice);
+    cudaGetLastError();
+    if (on_device)
+      ADA_CHECK_CUDA(cudaMemcpy(t.data.data(), data, n * 4, cudaMemcpyDeviceToHost));
+    else
+      memcpy(t.data.data(), data, n * 4);
+    h->host[key] = std::move(t);
+  });
+}
+
+int ada_finalize(ada_handle h) {
+  return guarded([&] {
+    ADA_REQUIRE(h, "null handle");
+    if (h->finalized) throw AdaError(ADA_ESTATE, "already finalized");
+    finalize_model(h);
+  });
+}
+
+int ada_forward(ada_handle h, const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
+                float* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  return guarded([&] {
+    ADA_REQUIRE(h && rgb && out, "null argument");
+    forward_impl(h, rgb, guides, guide_ch, n_guides, out, B, H, W, static_cast<cudaStream_t>(stream));
+  });
+}
+
+size_t ada_workspace_bytes(ada_handle h) { return h ? h->arena.bytes : 0; }
+
+int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W) {
+  if (!h) return -1;
+  (void)B; (void)H; (void)W;
+  if (h->last_launches > 0) return h->last_launches;
+  const ada_config& c = h->cfg;
+  // gather + cls + embed | per block: 2 LN + 4 GEMM + attention | 4 tap LN | head
+  int n = 3 + c.depth * 7 + 4;
+  n += 4 /*projects*/ + 2 /*convT*/ + 2 /*im2col+gemm*/ + 4 * 3 /*ip conv, LN, rn*/;
+  n += 3 * 6 + 4 /*refinenets: (2+2+1+1) x3, (2+1+1) for #4*/;
+  n += 3 /*oc1, upsample, tail*/;
+  if (h->capture) n += 0;
+  return n;
+}
+
+int ada_set_capture(ada_handle h, int32_t on) {
+  if (!h) return ADA_EINVAL;
+  h->capture = on != 0;
+  return ADA_OK;
+}
+
+int ada_read_intermediate(ada_handle h, const char* name, float* dst, int64_t count) {
+  return guarded([&] {
+    ADA_REQUIRE(h && name && dst, "null argument");
+    auto it = h->named.find(name);
+    ADA_REQUIRE(it != h->named.end(), std::string("unknown intermediate: ") + name);
+    ADA_REQUIRE(static_cast<size_t>(count) == it->second.second,
+                std::string(name) + " has " + std::to_string(it->second.second) + " elements");
+    cudaPointerAttributes attr;
+    bool dst_dev = false;
+    if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess) dst_dev = (attr.type == cudaMemoryTypeDevice);
+    cudaGetLastError();
+    float* tmp = dst;
+    if (!dst_dev) ADA_CHECK_CUDA(cudaMalloc(&tmp, count * 4));
+    if (h->named_is_f32[name]) {
+      ADA_CHECK_CUDA(cudaMemcpy(tmp, it->second.first, count * 4, cudaMemcpyDeviceToDevice));
+    } else {
+      bf16_to_f32_kernel<<<static_cast<unsigned>((count + 255) / 256), 256>>>(
+          static_cast<const __nv_bfloat16*>(it->second.first), tmp, count);
+      ADA_CHECK_CUDA(cudaGetLastError());
+    }
+    ADA_CHECK_CUDA(cudaDeviceSynchronize());
+    if (!dst_dev) {
+      ADA_CHECK_CUDA(cudaMemcpy(dst, tmp, count * 4, cudaMemcpyDeviceToHost));
+      cudaFree(tmp);
+    }
+  });
+}
+
+void ada_destroy(ada_handle h) { delete h; }
+
+int ada_interp_pos_embed_host(const float* pos_patch, int32_t grid, int32_t D, int32_t gh, int32_t gw, float offset,
+                              float* out) {
+  return guarded([&] {
+    ADA_REQUIRE(pos_patch && out && grid > 0 && D > 0 && gh > 0 && gw > 0, "bad argument");
+    interp_pos_host(pos_patch, grid, D, gh, gw, offset, out);
+  });
+}
+
+// ---- operator level
+int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(d && d->A && d->Bw, "null argument");
+    GemmLaunch L;
+    L.A = d->A;
+    L.Bw = d->Bw;
+    L.M = d->M;
+    L.N = d->N;
+    L.K = d->K;
+    L.lda = d->lda;
+    L.ldb = d->ldb;
+    L.a_mode = d->a_mode;
+    L.batch = d->batch;
+    L.H = d->H;
+    L.W = d->W;
+    L.Cin = d->Cin;
+    L.force_bn = d->force_bn;
+    GemmArgs& e = L.args;
+    e.epi = d->epi;
+    e.act = d->act;
+    e.bias = d->bias;
+    e.gamma = d->gamma;
+    e.resid_f32 = d->resid_f32;
+    e.out_f32 = d->out_f32;
+    e.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
+    e.out_relu = static_cast<__nv_bfloat16*>(d->out_relu);
+    e.resid1 = static_cast<const __nv_bfloat16*>(d->resid1);
+    e.resid2 = static_cast<const __nv_bfloat16*>(d->resid2);
+    e.aux = d->aux;
+    e.ldo = d->ldo;
+    e.P = d->P;
+    e.ks = d->ks;
+    e.cout = d->cout;
+    e.sigmoid = d->sigmoid;
+    if (d->epi == EPI_CONVT) {
+      e.H = d->H;
+      e.W = d->W;
+    }
+    launch_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_layernorm(const float* x, const float* w, const float* b, void* out_bf16, int32_t rows, int32_t D, float eps,
+                     int32_t n_tok, int32_t drop_cls, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_layernorm(x, w, b, static_cast<__nv_bfloat16*>(out_bf16), rows, D, eps, n_tok, drop_cls,
+                     static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, N, heads,
+                     static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_channel_ln_relu(const void* in_bf16, const float* w, const float* b, void* out_bf16, int64_t pixels, int32_t C,
+                           float eps, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_channel_ln_relu(static_cast<const __nv_bfloat16*>(in_bf16), w, b, static_cast<__nv_bfloat16*>(out_bf16), pixels,
+                           C, eps, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_upsample(const void* in_bf16, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                    int32_t C, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_upsample(static_cast<const __nv_bfloat16*>(in_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, Hi, Wi, Ho, Wo, C,
+                    static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_patch_gather(const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
+                        void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t Kpad, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_patch_gather(rgb, guides, guide_ch, n_guides, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, Kpad,
+                        static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_im2col_s2(static_cast<const __nv_bfloat16*>(in_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, H, W, C,
+                     static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_pack_conv3x3(const float* w_host, int32_t Cout, int32_t Cin, void* dst) {
+  return guarded([&] {
+    require_device();
+    std::vector<uint16_t> h = pack_conv3x3_host(w_host, Cout, Cin);
+    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  });
+}
+
+int ada_pack_convT(const float* w_host, int32_t Cin, int32_t Cout, int32_t ks, void* dst) {
+  return guarded([&] {
+    require_device();
+    std::vector<uint16_t> h = pack_convT_host(w_host, Cin, Cout, ks);
+    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  });
+}
+
+}  // extern "C"

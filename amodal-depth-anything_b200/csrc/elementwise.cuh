@@ -1,0 +1,225 @@
+// Bandwidth-bound kernels of the path: LayerNorm (token and channel), patch gather, cls rows, stride-2 im2col,
+// bilinear (align_corners=True) upsampling. All vectorised to 16-byte accesses, fp32 statistics.
+#pragma once
+#include "ptx.cuh"
+
+namespace ada {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Token LayerNorm: fp32 rows [rows, D] -> bf16 rows. One warp per row, the row lives in registers (two-pass stats).
+// Reference: nn.LayerNorm(D, eps=1e-6) block.py:84,87 and the shared final norm dinov2.py:337-338.
+// drop_cls != 0: input rows are [B, n_tok, D]; token 0 (cls) is skipped and the output is the dense patch map
+// [B, n_tok-1, D] == NHWC [B, h, w, D] (dinov2.py:339-340 + dpt.py:168-171 collapse into the store address).
+template <int CHUNKS>  // D = CHUNKS * 128
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                      __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls) {
+  constexpr int D = CHUNKS * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long orow = row;
+  if (drop_cls) {
+    const int bi = row / n_tok, t = row % n_tok;
+    if (t == 0) return;
+    orow = static_cast<long long>(bi) * (n_tok - 1) + (t - 1);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  float4 v[CHUNKS];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + c * c) + (d * d + e * e);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  uint2* o = reinterpret_cast<uint2*>(out + orow * D);
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x;
+    const float y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+    const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
+    const float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+    o[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channel LayerNorm + ReLU over NHWC bf16 pixels (channels_first LayerNorm of dpt.py:56-61 followed by nn.ReLU,
+// dpt.py:156-158). One warp per pixel, C % 8 == 0, C <= 8 * 32 * MAXG. In-place safe.
+template <int MAXG>
+__global__ void __launch_bounds__(256)
+channel_ln_relu_kernel(const __nv_bfloat16* in, const float* __restrict__ w, const float* __restrict__ b,
+                       __nv_bfloat16* out, long long pixels, int C, float eps) {
+  const long long pix = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= pixels) return;
+  const int groups = C >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(in + pix * C);
+  float v[MAXG][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    const int gi = lane + 32 * i;
+    if (gi < groups) {
+      const uint4 r = src[gi];
+      v[i][0] = bf16_lo(r.x); v[i][1] = bf16_hi(r.x); v[i][2] = bf16_lo(r.y); v[i][3] = bf16_hi(r.y);
+      v[i][4] = bf16_lo(r.z); v[i][5] = bf16_hi(r.z); v[i][6] = bf16_lo(r.w); v[i][7] = bf16_hi(r.w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    if (lane + 32 * i < groups) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  uint4* dst = reinterpret_cast<uint4*>(out + pix * C);
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    const int gi = lane + 32 * i;
+    if (gi < groups) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = (v[i][j] - mean) * rstd * __ldg(w + gi * 8 + j) + __ldg(b + gi * 8 + j);
+        y[j] = fmaxf(t, 0.0f);
+      }
+      dst[gi] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                           pack_bf16x2(y[6], y[7]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Patch gather: fp32 NCHW image planes -> bf16 A matrix [B*P, Kpad] of the 14x14/s14 patch-embed GEMM, with the
+// ImageNet normalisation of dav2.py:65 applied to the RGB planes (guide planes pass through, dav2.py:73-74).
+// K index = c*196 + ky*14 + kx, matching the [D, C, 14, 14] conv weight flattened (patch_embed.py:66).
+// Sources: up to 4 tensors, each [B, ch_i, H, W]; channel c of the concatenation is found by prefix sums.
+struct PatchSrc {
+  const float* ptr[4];
+  int ch[4];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+patch_gather_kernel(PatchSrc src, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int Kpad,
+                    float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int pw = W / 14, ph = H / 14;
+  const long long total = static_cast<long long>(B) * ph * C * 14 * pw;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // idx = (((b*ph + py)*C + c)*14 + ky)*pw + px   -> consecutive threads read consecutive 56-byte runs of one image row
+  const int px = static_cast<int>(idx % pw);
+  long long t = idx / pw;
+  const int ky = static_cast<int>(t % 14); t /= 14;
+  const int c = static_cast<int>(t % C); t /= C;
+  const int py = static_cast<int>(t % ph);
+  const int b = static_cast<int>(t / ph);
+  int cs = c, si = 0;
+  while (si < src.n - 1 && cs >= src.ch[si]) { cs -= src.ch[si]; ++si; }
+  const float* p = src.ptr[si] + ((static_cast<long long>(b) * src.ch[si] + cs) * H + (py * 14 + ky)) * W + px * 14;
+  float mean = 0.f, sd = 1.f;
+  if (c == 0) { mean = m0; sd = s0; } else if (c == 1) { mean = m1; sd = s1; } else if (c == 2) { mean = m2; sd = s2; }
+  __nv_bfloat16* o = out + (static_cast<long long>(b) * ph * pw + py * pw + px) * Kpad + (c * 14 + ky) * 14;
+  uint32_t* o2 = reinterpret_cast<uint32_t*>(o);  // (c*14+ky)*14 is even -> 4-byte aligned
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const float a = (p[2 * j] - mean) / sd;
+    const float d = (p[2 * j + 1] - mean) / sd;
+    o2[j] = pack_bf16x2(a, d);
+  }
+}
+
+// cls rows of the token stream: x[b, 0, :] = cls_token + pos_embed[0]  (dinov2.py:245-246)
+__global__ void cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ x, int B, int n_tok, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i % D;
+  x[static_cast<long long>(b) * n_tok * D + d] = cls_pos[d];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stride-2 3x3 pad-1 gather (resize_layers[3], dpt.py:102-107): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C], tap-major K.
+__global__ void __launch_bounds__(256)
+im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
+                 int Ho, int Wo) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * groups;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gi = static_cast<int>(idx % groups);
+  long long t = idx / groups;
+  const int tap = static_cast<int>(t % 9); t /= 9;
+  const int xo = static_cast<int>(t % Wo); t /= Wo;
+  const int yo = static_cast<int>(t % Ho);
+  const int b = static_cast<int>(t / Ho);
+  const int y = yo * 2 + tap / 3 - 1, x = xo * 2 + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (y >= 0 && y < H && x >= 0 && x < W)
+    v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * C + gi * 8);
+  *reinterpret_cast<uint4*>(out + idx * 8) = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear upsampling, align_corners=True (blocks.py:144, dpt.py:194), NHWC bf16. One thread per 8 channels.
+// Index math mirrors ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1).
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Hi, int Wi,
+                         int Ho, int Wo, int C) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gi = static_cast<int>(idx % groups);
+  long long t = idx / groups;
+  const int xo = static_cast<int>(t % Wo); t /= Wo;
+  const int yo = static_cast<int>(t % Ho);
+  const int b = static_cast<int>(t / Ho);
+  const float sh = (Ho > 1) ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const float fy = sh * yo, fx = sw * xo;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const __nv_bfloat16* base = in + static_cast<long long>(b) * Hi * Wi * C + gi * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * C);
+  const uint4 bq = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * C);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * C);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * C);
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {c.x, c.y, c.z, c.w},
+                 dv[4] = {d.x, d.y, d.z, d.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float lo = hy * (hx * bf16_lo(av[j]) + lx * bf16_lo(bv[j])) + ly * (hx * bf16_lo(cv[j]) + lx * bf16_lo(dv[j]));
+    const float hi = hy * (hx * bf16_hi(av[j]) + lx * bf16_hi(bv[j])) + ly * (hx * bf16_hi(cv[j]) + lx * bf16_hi(dv[j]));
+    o[j] = pack_bf16x2(lo, hi);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace ada

@@ -1,0 +1,384 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * B[N,K]^T).
+//
+//   warp 0      : TMA producer  (A and B tiles, 128-byte swizzle, 4..8 stage mbarrier ring)
+//   warp 1      : MMA issuer    (tcgen05.mma cta_group::1, 128 x BN x 16, fp32 accumulators in TMEM, 2 accumulator stages)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// The A operand is fetched either as a plain row-major matrix (linear layers, 1x1 convs, transposed convs with k == s)
+// or as an implicit-GEMM 3x3/pad-1/stride-1 convolution over an NHWC map: the M tile is an 8x16 pixel patch and each
+// of the 9 taps is one shifted 4-D TMA box whose out-of-bounds part the hardware zero-fills (that is the padding).
+//
+// Reference ops this kernel replaces (all fp32 torch ops in the reference):
+//   attention.py:51,60  mlp.py:36-39  swiglu_ffn.py:30-33  layer_scale.py:28  block.py:105-106   (encoder linears)
+//   patch_embed.py:76   dinov2.py:234-246                                                       (patch embed + pos)
+//   dpt.py:172-173,178  blocks.py:20-24,57-80,146  dpt.py:193,195                                (DPT head convs)
+#pragma once
+#include "ptx.cuh"
+
+namespace ada {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTileH = 8;     // conv mode: M tile = 8 x 16 pixels
+constexpr int kTileW = 16;
+constexpr int kGemmThreads = 256;
+
+enum EpiMode : int {
+  EPI_BF16 = 0,       // out_bf16 = act(acc + bias) [+ resid1 + resid2]; optional second copy with ReLU applied
+  EPI_RESID_F32 = 1,  // out_f32 = resid_f32 + gamma * (acc + bias)          (LayerScale + residual, fp32 stream)
+  EPI_EMBED = 2,      // out_f32[b*(P+1)+1+p, :] = acc + aux[p, :]           (patch embed: + bias + pos-embed, skip cls row)
+  EPI_CONVT = 3,      // k == s transposed conv: pixel-shuffle scatter, + bias[co]
+  EPI_TAIL = 4,       // sigmoid(relu(acc + bias) . aux[0:32] + aux[32]) -> fp32 per pixel (BN must be 32)
+  EPI_SWIGLU = 5      // columns interleaved in 32-wide (x1, x2) chunk pairs: out = silu(x1 + b1) * (x2 + b2)
+};
+enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1 };
+
+struct GemmArgs {
+  int M, N, K;          // logical problem (conv mode: M = B*H*W pixels, K = 9 * c_pad)
+  int a_mode;
+  int epi, act;
+  // conv geometry (A_CONV3X3) -- also used by EPI_CONVT for the input grid
+  int H, W, tiles_x, tiles_y, c_chunks;  // c_chunks = c_pad / 64
+  // epilogue operands
+  const float* bias;        // [N] (EPI_CONVT: [Cout]) or nullptr
+  const float* gamma;       // [N]
+  const float* resid_f32;   // may alias out_f32
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_relu;  // optional relu(out) copy
+  const __nv_bfloat16* resid1;
+  const __nv_bfloat16* resid2;
+  const float* aux;
+  int ldo;                  // output row pitch in elements
+  int P;                    // EPI_EMBED: patches per image
+  int ks, cout;             // EPI_CONVT: kernel == stride, output channels
+  int sigmoid;              // EPI_TAIL
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KB alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout: full[kStages], empty[kStages], tfull[2], tempty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int tiles_m = (g.a_mode == A_CONV3X3) ? (g.M / (g.H * g.W)) * g.tiles_x * g.tiles_y
+                                              : (g.M + kBlockM - 1) / kBlockM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (g.a_mode == A_CONV3X3) ? 9 * g.c_chunks : (g.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / tiles_n, nt = t % tiles_n;
+      int img = 0, y0 = 0, x0 = 0;
+      if (g.a_mode == A_CONV3X3) {
+        const int per_img = g.tiles_x * g.tiles_y;
+        img = mt / per_img;
+        const int r = mt % per_img;
+        y0 = (r / g.tiles_x) * kTileH;
+        x0 = (r % g.tiles_x) * kTileW;
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (g.a_mode == A_CONV3X3) {
+            const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
+            const int ky = tap / 3, kx = tap % 3;
+            tma_load_4d(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, mt * kBlockM);
+          }
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, nt * BN);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200 + acc);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase, 0x300 + stage);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaK * 2, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaK * 2, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // accumulator row owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / tiles_n, nt = t % tiles_n;
+      const int n0 = nt * BN;
+      // ---- map accumulator row -> output row
+      bool valid;
+      long long orow;  // output row index (pixels / tokens)
+      int m;           // logical A row (used by EMBED / CONVT)
+      if (g.a_mode == A_CONV3X3) {
+        const int per_img = g.tiles_x * g.tiles_y;
+        const int img = mt / per_img;
+        const int r = mt % per_img;
+        const int y = (r / g.tiles_x) * kTileH + row / kTileW;
+        const int x = (r % g.tiles_x) * kTileW + row % kTileW;
+        valid = (y < g.H) && (x < g.W);
+        orow = (static_cast<long long>(img) * g.H + y) * g.W + x;
+        m = static_cast<int>(orow);
+      } else {
+        m = mt * kBlockM + row;
+        valid = m < g.M;
+        orow = m;
+      }
+      if (g.epi == EPI_EMBED) {
+        const int b = m / g.P, p = m % g.P;
+        orow = static_cast<long long>(b) * (g.P + 1) + 1 + p;
+      }
+
+      mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      if (g.epi == EPI_TAIL) {
+        if constexpr (BN == 32) {
+          uint32_t r[32];
+          tmem_ld32(t_addr, r);
+          tmem_ld_wait();
+          float s = __ldg(g.aux + 32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + __ldg(g.bias + j);
+            v = fmaxf(v, 0.0f);
+            s = fmaf(v, __ldg(g.aux + j), s);
+          }
+          if (g.sigmoid) s = 1.0f / (1.0f + __expf(-s));
+          if (valid) g.out_f32[orow] = s;
+        }
+      } else if (g.epi == EPI_SWIGLU) {
+        // chunk pairs: even 32-col chunk = x1, odd = x2 (weights were interleaved at pack time)
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t a[32], b[32];
+          tmem_ld32(t_addr + c * 64, a);
+          tmem_ld32(t_addr + c * 64 + 32, b);
+          tmem_ld_wait();
+          const int nb = n0 + c * 64;          // interleaved column of x1 chunk
+          const int on = (n0 >> 1) + c * 32;   // output column
+          if (valid && nb < g.N) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float x1a = __uint_as_float(a[j]) + __ldg(g.bias + nb + j);
+              float x1b = __uint_as_float(a[j + 1]) + __ldg(g.bias + nb + j + 1);
+              float x2a = __uint_as_float(b[j]) + __ldg(g.bias + nb + 32 + j);
+              float x2b = __uint_as_float(b[j + 1]) + __ldg(g.bias + nb + 32 + j + 1);
+              float ha = x1a / (1.0f + __expf(-x1a)) * x2a;
+              float hb = x1b / (1.0f + __expf(-x1b)) * x2b;
+              pk[j >> 1] = pack_bf16x2(ha, hb);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + orow * g.ldo + on);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c * 32, r);
+          tmem_ld_wait();
+          const int nb = n0 + c * 32;
+          if (!valid || nb >= g.N) continue;
+          if (g.epi == EPI_RESID_F32) {
+            const float* rs = g.resid_f32 + orow * g.ldo + nb;
+            float* dst = g.out_f32 + orow * g.ldo + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nb + j < g.N) {
+                const float4 xr = *reinterpret_cast<const float4*>(rs + j);
+                const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                const float4 ga = __ldg(reinterpret_cast<const float4*>(g.gamma + nb + j));
+                float4 o;
+                o.x = fmaf(ga.x, __uint_as_float(r[j]) + bi.x, xr.x);
+                o.y = fmaf(ga.y, __uint_as_float(r[j + 1]) + bi.y, xr.y);
+                o.z = fmaf(ga.z, __uint_as_float(r[j + 2]) + bi.z, xr.z);
+                o.w = fmaf(ga.w, __uint_as_float(r[j + 3]) + bi.w, xr.w);
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            }
+          } else if (g.epi == EPI_EMBED) {
+            const int p = m % g.P;
+            const float* ax = g.aux + static_cast<long long>(p) * g.N + nb;
+            float* dst = g.out_f32 + orow * g.ldo + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nb + j < g.N) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ax + j));
+                float4 o;
+                o.x = __uint_as_float(r[j]) + a4.x;
+                o.y = __uint_as_float(r[j + 1]) + a4.y;
+                o.z = __uint_as_float(r[j + 2]) + a4.z;
+                o.w = __uint_as_float(r[j + 3]) + a4.w;
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            }
+          } else {
+            // EPI_BF16 / EPI_CONVT: 8-column groups, one 16-byte store each
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              const int n = nb + gi * 8;
+              if (n >= g.N) break;
+              float v[8];
+              long long off;
+              const float* bptr;
+              if (g.epi == EPI_CONVT) {
+                const int kk = n / g.cout, co = n % g.cout;
+                const int ky = kk / g.ks, kx = kk % g.ks;
+                const int hw = g.H * g.W;
+                const int b = m / hw, rem = m % hw;
+                const int y = rem / g.W, x = rem % g.W;
+                off = ((static_cast<long long>(b) * g.H * g.ks + y * g.ks + ky) * (g.W * g.ks) + x * g.ks + kx) *
+                          g.cout + co;
+                bptr = g.bias ? g.bias + co : nullptr;
+              } else {
+                off = orow * g.ldo + n;
+                bptr = g.bias ? g.bias + n : nullptr;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gi * 8 + j]);
+              if (bptr) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (g.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              } else if (g.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+              if (g.resid1) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(g.resid1 + off);
+                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+              }
+              if (g.resid2) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(g.resid2 + off);
+                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+              }
+              if (g.out_bf16) {
+                *reinterpret_cast<uint4*>(g.out_bf16 + off) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                               pack_bf16x2(v[6], v[7]));
+              }
+              if (g.out_relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                *reinterpret_cast<uint4*>(g.out_relu + off) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                               pack_bf16x2(v[6], v[7]));
+              }
+            }
+          }
+        }
+      }
+      // accumulator stage drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace ada

@@ -1,0 +1,111 @@
+"""Operator-level wrappers over the C ABI, taking torch CUDA tensors. Used by tests/ and tools/ to check each kernel
+against the matching torch op; the model path (model.py) calls ada_forward directly and does not go through here."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,
+         out_relu=None, resid1=None, resid2=None, aux=None, ldo=0, P=0, ks=0, cout=0, sigmoid=0, force_bn=0,
+         conv=None, N=None, K=None, M=None, H=0, W=0):
+    """A: bf16 [M,K] (linear) or NHWC bf16 [B,H,W,Cin] (conv=(B,H,W,Cin)); Wt: bf16 [N,Kw]."""
+    lib = L.load()
+    d = L.GemmDesc()
+    d.A, d.Bw = A.data_ptr(), Wt.data_ptr()
+    if conv is not None:
+        B_, H_, W_, Cin = conv
+        d.a_mode, d.batch, d.H, d.W, d.Cin = L.A_CONV3X3, B_, H_, W_, Cin
+        d.M, d.K, d.lda = B_ * H_ * W_, 0, 0
+    else:
+        d.a_mode = L.A_LINEAR
+        d.M = M if M is not None else A.shape[0]
+        d.K = K if K is not None else A.shape[1]
+        d.lda = A.stride(0)
+        d.H, d.W = H, W
+    d.N = N if N is not None else Wt.shape[0]
+    d.ldb = Wt.stride(0)
+    d.epi, d.act = epi, act
+    for name, t in (("bias", bias), ("gamma", gamma), ("resid_f32", resid_f32), ("out_f32", out_f32),
+                    ("out_bf16", out_bf16), ("out_relu", out_relu), ("resid1", resid1), ("resid2", resid2), ("aux", aux)):
+        setattr(d, name, t.data_ptr() if t is not None else None)
+    d.ldo, d.P, d.ks, d.cout, d.sigmoid, d.force_bn = ldo, P, ks, cout, sigmoid, force_bn
+    L.check(lib.ada_op_gemm(ctypes.byref(d), _stream()))
+
+
+def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False):
+    rows, D = x.shape
+    if drop_cls:
+        out = torch.empty((rows // n_tok) * (n_tok - 1), D, dtype=torch.bfloat16, device=x.device)
+    else:
+        out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().ada_op_layernorm(_p(x), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls), _stream()))
+    return out
+
+
+def attention(qkv, B, N, heads):
+    out = torch.empty(B * N, heads * 64, dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.load().ada_op_attention(_p(qkv), _p(out), B, N, heads, _stream()))
+    return out
+
+
+def channel_ln_relu(x_nhwc, w, b, eps=1e-6):
+    C = x_nhwc.shape[-1]
+    out = torch.empty_like(x_nhwc)
+    L.check(L.load().ada_op_channel_ln_relu(_p(x_nhwc), _p(w), _p(b), _p(out), x_nhwc.numel() // C, C, eps, _stream()))
+    return out
+
+
+def upsample(x_nhwc, Ho, Wo):
+    B, Hi, Wi, C = x_nhwc.shape
+    out = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x_nhwc.device)
+    L.check(L.load().ada_op_upsample(_p(x_nhwc), _p(out), B, Hi, Wi, Ho, Wo, C, _stream()))
+    return out
+
+
+def patch_gather(rgb, guides, Kpad):
+    B, _, H, W = rgb.shape
+    out = torch.zeros(B * (H // 14) * (W // 14), Kpad, dtype=torch.bfloat16, device=rgb.device)
+    n = len(guides)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[g.data_ptr() for g in guides])
+    chs = (ctypes.c_int32 * max(n, 1))(*[g.shape[1] for g in guides])
+    L.check(L.load().ada_op_patch_gather(_p(rgb), ptrs, chs, n, _p(out), B, H, W, Kpad, _stream()))
+    return out
+
+
+def im2col_s2(x_nhwc):
+    B, H, W, C = x_nhwc.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device=x_nhwc.device)
+    L.check(L.load().ada_op_im2col_s2(_p(x_nhwc), _p(out), B, H, W, C, _stream()))
+    return out
+
+
+def pack_conv3x3(w):
+    """torch conv weight [Cout,Cin,3,3] fp32 (any device) -> packed bf16 [Cout, 9*round_up(Cin,64)] on cuda."""
+    Cout, Cin = w.shape[:2]
+    Cpad = (Cin + 63) // 64 * 64
+    wh = w.detach().float().cpu().contiguous()
+    out = torch.empty(Cout, 9 * Cpad, dtype=torch.bfloat16, device="cuda")
+    L.check(L.load().ada_pack_conv3x3(_p(wh), Cout, Cin, _p(out)))
+    return out
+
+
+def pack_convT(w, ks):
+    """torch ConvTranspose2d weight [Cin,Cout,ks,ks] -> packed bf16 [ks*ks*Cout, Cin] on cuda."""
+    Cin, Cout = w.shape[:2]
+    wh = w.detach().float().cpu().contiguous()
+    out = torch.empty(ks * ks * Cout, Cin, dtype=torch.bfloat16, device="cuda")
+    L.check(L.load().ada_pack_convT(_p(wh), Cin, Cout, ks, _p(out)))
+    return out

@@ -1,0 +1,126 @@
+/* amodal_b200.h -- C ABI of libamodal_b200.so: the B200 (sm_100a) implementation of the discriminative forward pass of
+ * Amodal-Depth-Anything (guided Depth-Anything-V2).
+ *
+ * The reference has no FFI of its own; its boundary for this path is the Python class
+ *   AmodalDAv2.forward(x, guide_rgb, guide_mask, observation)      src/models/amodalsynthdrive/dav2.py:64-85
+ *   DepthAnythingV2.forward(x, guidance_mask)                      .../depth_anything_v2/dpt.py:225-231
+ * Every entry point below names the reference code it replaces. All pointers are plain device (or, where stated, host)
+ * pointers; no torch types cross this boundary. Functions return 0 on success and a negative ADA_E* code on failure;
+ * ada_last_error() returns a thread-local human readable reason. Nothing throws across the ABI.
+ * There is no CPU fallback: compute entry points fail with ADA_ENODEVICE when no sm_100 device is usable.
+ */
+#ifndef AMODAL_B200_H
+#define AMODAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADA_OK 0
+#define ADA_EINVAL (-1)     /* bad argument / unknown weight key / wrong shape */
+#define ADA_ENODEVICE (-2)  /* no CUDA device, or device is not sm_100 */
+#define ADA_ECUDA (-3)      /* a CUDA call or kernel failed; see ada_last_error() */
+#define ADA_ESTATE (-4)     /* called in the wrong order (e.g. forward before finalize) */
+
+typedef struct ada_model* ada_handle;
+
+/* Architecture description == the constructor arguments of DepthAnythingV2 (dpt.py:201-223) + DINOv2() (dinov2.py:430-448). */
+typedef struct ada_config {
+  int32_t embed_dim;         /* 384 / 768 / 1024 / 1536                      dinov2.py:370-420 */
+  int32_t depth;             /* 12 / 12 / 24 / 40 */
+  int32_t num_heads;         /* embed_dim / 64 */
+  int32_t ffn_kind;          /* 0 = Mlp fc1-GELU-fc2 (mlp.py:35-41), 1 = SwiGLUFFNFused (swiglu_ffn.py:29-33,45-63) */
+  int32_t ffn_hidden;        /* 4*embed_dim (Mlp) or 4096 (SwiGLU @1536) */
+  int32_t taps[4];           /* intermediate_layer_idx                       dpt.py:213-218 */
+  int32_t features;          /* DPT feature width F                          dav2.py:32-34 */
+  int32_t out_channels[4];   /* reassemble widths C_i                        dav2.py:32-34 */
+  int32_t guide_channels;    /* channels of patch_embed_guidance (0 = 'none') dinov2.py:110-125 */
+  int32_t sigmoid;           /* 1 unless 'ssi' in loss_stategy               dpt.py:138-151 */
+  int32_t pos_grid;          /* sqrt(num_patches) of pos_embed = 37          dinov2.py:437 */
+  float interpolate_offset;  /* 0.1                                          dinov2.py:446 */
+} ada_config;
+
+/* ---- model lifetime -------------------------------------------------------------------------------------------- */
+/* Replaces AmodalDAv2.__init__ / DepthAnythingV2.__init__ (dav2.py:22-61, dpt.py:201-223): creates an empty model. */
+int ada_create(const ada_config* cfg, ada_handle* out);
+/* Replaces nn.Module.load_state_dict for one tensor: `key` is the reference state-dict name relative to
+ * `encoder.` (e.g. "pretrained.blocks.3.attn.qkv.weight", "depth_head.scratch.layer1_rn.weight"); data is fp32,
+ * contiguous, host or device memory (copied; the caller keeps ownership). Shapes are checked against the config. */
+int ada_set_weight(ada_handle h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+/* Packs weights for the kernels: bf16 K-major GEMM operands, fused (3+Cg)-channel patch-embed weight, tap-major conv
+ * weights, pre-added biases. Fails with ADA_ESTATE and lists missing keys if the state dict is incomplete. */
+int ada_finalize(ada_handle h);
+/* Replaces AmodalDAv2.forward (dav2.py:64-85) in eval mode. rgb: [B,3,H,W] fp32 in [0,1] (ImageNet normalisation is
+ * applied inside, dav2.py:65). guides[i]: [B,guide_ch[i],H,W] fp32, concatenated in order along channels (dav2.py:67-76);
+ * sum(guide_ch) must equal cfg.guide_channels. out: [B,1,H,W] fp32. All device pointers, NCHW contiguous.
+ * H and W must be multiples of 14 (patch_embed.py:73-74). Asynchronous on `stream` (a cudaStream_t); no host sync. */
+int ada_forward(ada_handle h, const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
+                float* out, int32_t B, int32_t H, int32_t W, void* stream);
+/* Bytes of device workspace the handle holds for its largest (B,H,W) so far. */
+size_t ada_workspace_bytes(ada_handle h);
+/* Number of kernels one ada_forward at (B,H,W) launches (for bench.py's gpu_launches). */
+int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W);
+/* Test hook: copy a named intermediate of the LAST forward to `dst` (device or host fp32, `count` elements).
+ * Names: "tap0".."tap3" ([B,h*w,D] normalised patch tokens, dinov2.py:337-340), "layer1_rn".."layer4_rn",
+ * "path_1".."path_4" (NHWC), "tokens" (x after prepare_tokens_with_masks; needs ada_set_capture(h,1)). */
+int ada_read_intermediate(ada_handle h, const char* name, float* dst, int64_t count);
+int ada_set_capture(ada_handle h, int32_t on);
+void ada_destroy(ada_handle h);
+const char* ada_last_error(void);
+/* Device error mailbox written by a kernel that timed out on a barrier (4 words: code, block, parity, thread). */
+int ada_device_error(uint32_t out[4]);
+
+/* ---- host utility (runs on the CPU; no device needed) -------------------------------------------------------- */
+/* Replaces interpolate_pos_encoding (dinov2.py:199-230): bicubic (A=-0.75, align_corners=False, scale_factor =
+ * (gh+off)/grid, (gw+off)/grid) resampling of the [grid*grid, D] patch position table to [gh*gw, D]. Host pointers. */
+int ada_interp_pos_embed_host(const float* pos_patch, int32_t grid, int32_t D, int32_t gh, int32_t gw, float offset,
+                              float* out);
+
+/* ---- operator-level entry points (used by tests/ to check each kernel against torch on the same data) --------- */
+typedef struct ada_gemm_desc {
+  const void* A;        /* bf16 [M,K] row-major (lda) or, conv mode, NHWC [B,H,W,Cin] */
+  const void* Bw;       /* bf16 [N,K] row-major (ldb): the torch Linear / packed conv weight */
+  int32_t M, N, K, lda, ldb;
+  int32_t a_mode;       /* 0 linear, 1 conv3x3 (pad 1, stride 1) */
+  int32_t epi, act;     /* see EpiMode / ActMode in csrc/gemm.cuh */
+  int32_t batch, H, W, Cin;   /* conv mode geometry; EPI_CONVT: input grid */
+  const float* bias;
+  const float* gamma;
+  const float* resid_f32;
+  float* out_f32;
+  void* out_bf16;
+  void* out_relu;
+  const void* resid1;
+  const void* resid2;
+  const float* aux;
+  int32_t ldo, P, ks, cout, sigmoid;
+  int32_t force_bn;     /* 0 = auto, else 32/64/128/256 */
+} ada_gemm_desc;
+int ada_op_gemm(const ada_gemm_desc* d, void* stream);
+/* out[rows or B*(n_tok-1), D] bf16 = LayerNorm(x fp32 [rows, D]) (block.py:84,87; dinov2.py:337-340 when drop_cls). */
+int ada_op_layernorm(const float* x, const float* w, const float* b, void* out_bf16, int32_t rows, int32_t D, float eps,
+                     int32_t n_tok, int32_t drop_cls, void* stream);
+/* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
+int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
+/* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */
+int ada_op_channel_ln_relu(const void* in_bf16, const float* w, const float* b, void* out_bf16, int64_t pixels, int32_t C,
+                           float eps, void* stream);
+/* NHWC bf16 bilinear, align_corners=True (blocks.py:144, dpt.py:194). */
+int ada_op_upsample(const void* in_bf16, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                    int32_t C, void* stream);
+/* fp32 NCHW planes -> bf16 patch matrix [B*P, Kpad] (dav2.py:65,73-74 + patch_embed.py:76 im2col-free gather). */
+int ada_op_patch_gather(const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
+                        void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t Kpad, void* stream);
+/* stride-2 3x3 gather for resize_layers[3] (dpt.py:102-107): NHWC -> [B*Ho*Wo, 9*C]. */
+int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* Weight packers (host fp32 in, device bf16 out) -- the same code ada_finalize uses. */
+int ada_pack_conv3x3(const float* w_host, int32_t Cout, int32_t Cin, void* dst_dev_bf16 /* [Cout, 9*round_up(Cin,64)] */);
+int ada_pack_convT(const float* w_host, int32_t Cin, int32_t Cout, int32_t ks, void* dst_dev_bf16 /* [ks*ks*Cout, Cin] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMODAL_B200_H */

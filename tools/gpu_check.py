@@ -1,0 +1,301 @@
+"""Bring-up harness: runs each kernel check in its own subprocess (a trapped kernel poisons its CUDA context) and writes
+gpurun_out/gpu_check.json. `python tools/gpu_check.py` runs all; `--one NAME` runs a single check in-process."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _imports():
+    import torch
+    import amodal_depth_anything_b200  # noqa: F401
+    from amodal_depth_anything_b200 import _lib as L, ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch, L, ops
+
+
+def _cmp(name, got, ref, atol, rtol):
+    import torch
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    res = {"max_abs": err.max().item(), "max_ref": ref.abs().max().item(), "bad": bad, "n": ref.numel(),
+           "nan": int(torch.isnan(got).sum().item())}
+    res["ok"] = bad == 0 and res["nan"] == 0
+    return res
+
+
+def chk_gemm(M, N, K, bn, epi_name):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = (torch.randn(M, K, generator=g, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(N, K, generator=g, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g, device="cuda") * 0.1
+    ref = A.float() @ Wt.float().t() + bias
+    if epi_name == "bias":
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, force_bn=bn)
+    elif epi_name == "gelu":
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, act=L.ACT_GELU, force_bn=bn)
+        ref = torch.nn.functional.gelu(ref)
+    elif epi_name == "resid":
+        gamma = torch.randn(N, generator=g, device="cuda")
+        x = torch.randn(M, N, generator=g, device="cuda")
+        ref = x + gamma * ref
+        out = x.clone()
+        ops.gemm(A, Wt, epi=L.EPI_RESID_F32, bias=bias, gamma=gamma, resid_f32=out, out_f32=out, ldo=N, force_bn=bn)
+    elif epi_name == "swiglu":
+        Hd = N // 2
+        # interleave rows in 32-chunks exactly like ada_finalize does
+        idx = torch.arange(N, device="cuda")
+        chunk, within = idx // 64, idx % 64
+        src = torch.where(within < 32, chunk * 32 + within, Hd + chunk * 32 + within - 32)
+        out = torch.zeros(M, Hd, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(A, Wt[src].contiguous(), epi=L.EPI_SWIGLU, bias=bias[src].contiguous(), out_bf16=out, ldo=Hd, force_bn=bn)
+        x1, x2 = ref[:, :Hd], ref[:, Hd:]
+        ref = torch.nn.functional.silu(x1) * x2
+    torch.cuda.synchronize()
+    return _cmp("gemm", out, ref, 2e-2, 1e-2)
+
+
+def chk_embed():
+    torch, L, ops = _imports()
+    B, P, D, K = 2, 1369, 384, 1024
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = (torch.randn(B * P, K, generator=g, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(D, K, generator=g, device="cuda") * 0.05).bfloat16()
+    posb = torch.randn(P, D, generator=g, device="cuda")
+    x = torch.full((B * (P + 1), D), 7.0, device="cuda")
+    ops.gemm(A, Wt, epi=L.EPI_EMBED, aux=posb, out_f32=x, ldo=D, P=P)
+    torch.cuda.synchronize()
+    ref = (A.float() @ Wt.float().t()).view(B, P, D) + posb
+    got = x.view(B, P + 1, D)
+    r = _cmp("embed", got[:, 1:], ref, 1e-2, 1e-3)
+    r["cls_untouched"] = bool((got[:, 0] == 7.0).all().item())
+    r["ok"] = r["ok"] and r["cls_untouched"]
+    return r
+
+
+def chk_conv(B, H, W, Cin, Cout, mode):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn(B, Cin, H, W, generator=g, device="cuda")).bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, device="cuda") * (1.0 / (3 * Cin ** 0.5))
+    bias = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv3x3(w)
+    wq = w.bfloat16().float()
+    ref = torch.nn.functional.conv2d(x.float(), wq, bias, padding=1)
+    if mode == "plain":
+        out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, bias=bias, out_bf16=out, ldo=Cout)
+        torch.cuda.synchronize()
+        return _cmp("conv", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
+    if mode == "rcu":  # relu act + two residuals + relu copy
+        r1 = torch.randn(B, H, W, Cout, generator=g, device="cuda").bfloat16()
+        r2 = torch.randn(B, H, W, Cout, generator=g, device="cuda").bfloat16()
+        out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+        outr = torch.zeros_like(out)
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, bias=bias, act=L.ACT_RELU, resid1=r1, resid2=r2, out_bf16=out,
+                 out_relu=outr, ldo=Cout)
+        torch.cuda.synchronize()
+        ref2 = torch.relu(ref).permute(0, 2, 3, 1) + r1.float() + r2.float()
+        a = _cmp("conv", out, ref2, 3e-2, 1e-2)
+        b = _cmp("conv", outr, torch.relu(ref2), 3e-2, 1e-2)
+        a["relu_copy_ok"] = b["ok"]
+        a["ok"] = a["ok"] and b["ok"]
+        return a
+    if mode == "tail":
+        assert Cout == 32
+        w2 = torch.randn(32, generator=g, device="cuda") * 0.3
+        b2 = torch.randn(1, generator=g, device="cuda") * 0.1
+        aux = torch.cat([w2, b2]).contiguous()
+        out = torch.zeros(B, H, W, dtype=torch.float32, device="cuda")
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=32, epi=L.EPI_TAIL, bias=bias, aux=aux, out_f32=out, sigmoid=1)
+        torch.cuda.synchronize()
+        z = (torch.relu(ref) * w2.view(1, 32, 1, 1)).sum(1) + b2
+        return _cmp("tail", out, torch.sigmoid(z), 5e-3, 0)
+
+
+def chk_convT(ks):
+    torch, L, ops = _imports()
+    B, H, W, Cin, Cout = 2, 37, 37, 96, 96
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(B, Cin, H, W, generator=g, device="cuda").bfloat16()
+    w = torch.randn(Cin, Cout, ks, ks, generator=g, device="cuda") * 0.1
+    bias = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    ref = torch.nn.functional.conv_transpose2d(x.float(), w.bfloat16().float(), bias, stride=ks)
+    xa = x.permute(0, 2, 3, 1).reshape(B * H * W, Cin).contiguous()
+    wp = ops.pack_convT(w, ks)
+    out = torch.zeros(B, H * ks, W * ks, Cout, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(xa, wp, epi=L.EPI_CONVT, bias=bias, out_bf16=out, ks=ks, cout=Cout, H=H, W=W)
+    torch.cuda.synchronize()
+    return _cmp("convT", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
+
+
+def chk_attention(B, N, heads):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D = heads * 64
+    qkv = (torch.randn(B, N, 3, heads, 64, generator=g, device="cuda") * 1.5).bfloat16()
+    out = ops.attention(qkv, B, N, heads)
+    torch.cuda.synchronize()
+    q, k, v = [t.float().permute(0, 2, 1, 3) for t in qkv.unbind(2)]  # [B,h,N,64]
+    att = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+    return _cmp("attention", out, ref, 2e-2, 2e-2)
+
+
+def chk_layernorm(D, drop):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, n_tok = 3, 50
+    x = torch.randn(B * n_tok, D, generator=g, device="cuda") * 2 + 0.5
+    w = torch.randn(D, generator=g, device="cuda")
+    b = torch.randn(D, generator=g, device="cuda")
+    out = ops.layernorm(x, w, b, 1e-6, n_tok, drop)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-6)
+    if drop:
+        ref = ref.view(B, n_tok, D)[:, 1:].reshape(-1, D)
+    return _cmp("ln", out, ref, 2e-2, 1e-2)
+
+
+def chk_channel_ln(C):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(2, 9, 11, C, generator=g, device="cuda") * 2 + 0.3).bfloat16()
+    w = torch.randn(C, generator=g, device="cuda")
+    b = torch.randn(C, generator=g, device="cuda")
+    out = ops.channel_ln_relu(x, w, b)
+    torch.cuda.synchronize()
+    xf = x.float()
+    u = xf.mean(-1, keepdim=True)
+    s = (xf - u).pow(2).mean(-1, keepdim=True)
+    ref = torch.relu((xf - u) / torch.sqrt(s + 1e-6) * w + b)
+    return _cmp("cln", out, ref, 2e-2, 1e-2)
+
+
+def chk_upsample(Hi, Ho):
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(2, Hi, Hi, 64, generator=g, device="cuda").bfloat16()
+    out = ops.upsample(x, Ho, Ho)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), (Ho, Ho), mode="bilinear", align_corners=True)
+    return _cmp("up", out.permute(0, 3, 1, 2), ref, 2e-2, 1e-2)
+
+
+def chk_patch_gather():
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, W = 2, 70, 98
+    rgb = torch.rand(B, 3, H, W, generator=g, device="cuda")
+    m = torch.rand(B, 1, H, W, generator=g, device="cuda") * 2 - 1
+    o = torch.rand(B, 1, H, W, generator=g, device="cuda") * 2 - 1
+    out = ops.patch_gather(rgb, [m, o], 1024)
+    torch.cuda.synchronize()
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    x = torch.cat([(rgb - mean) / std, m, o], 1)
+    ref = torch.nn.functional.unfold(x, 14, stride=14).transpose(1, 2).reshape(B * (H // 14) * (W // 14), 5 * 196)
+    r = _cmp("gather", out[:, :980], ref, 1e-6, 2 ** -8)
+    r["pad_zero"] = bool((out[:, 980:] == 0).all().item())
+    r["ok"] = r["ok"] and r["pad_zero"]
+    return r
+
+
+def chk_im2col():
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, H, W, C = 2, 37, 37, 64
+    x = torch.randn(B, H, W, C, generator=g, device="cuda").bfloat16()
+    out = ops.im2col_s2(x)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L] (c-major)
+    Ho = (H - 1) // 2 + 1
+    ref = ref.view(B, C, 9, Ho * Ho).permute(0, 3, 2, 1).reshape(B * Ho * Ho, 9 * C)
+    return _cmp("im2col", out, ref, 0, 0)
+
+
+CHECKS = {
+    "gemm_small_bn128": lambda: chk_gemm(300, 256, 128, 128, "bias"),
+    "gemm_small_bn256": lambda: chk_gemm(300, 256, 128, 256, "bias"),
+    "gemm_small_bn64": lambda: chk_gemm(300, 256, 192, 64, "bias"),
+    "gemm_small_bn32": lambda: chk_gemm(300, 96, 64, 32, "bias"),
+    "gemm_qkv_shape": lambda: chk_gemm(1370 * 2, 3072, 1024, 0, "bias"),
+    "gemm_fc1_gelu": lambda: chk_gemm(1370, 4096, 1024, 0, "gelu"),
+    "gemm_fc2_resid": lambda: chk_gemm(1370, 1024, 4096, 0, "resid"),
+    "gemm_ragged_n": lambda: chk_gemm(500, 48, 384, 0, "bias"),
+    "gemm_swiglu": lambda: chk_gemm(700, 1024, 256, 0, "swiglu"),
+    "gemm_embed": chk_embed,
+    "conv_plain_37": lambda: chk_conv(2, 37, 37, 128, 64, "plain"),
+    "conv_c48": lambda: chk_conv(1, 20, 33, 48, 48, "plain"),
+    "conv_rcu": lambda: chk_conv(2, 19, 19, 64, 64, "rcu"),
+    "conv_tail": lambda: chk_conv(1, 70, 84, 64, 32, "tail"),
+    "convT_k4": lambda: chk_convT(4),
+    "convT_k2": lambda: chk_convT(2),
+    "attention_small": lambda: chk_attention(1, 128, 1),
+    "attention_ragged": lambda: chk_attention(1, 200, 2),
+    "attention_1370": lambda: chk_attention(2, 1370, 6),
+    "layernorm_384": lambda: chk_layernorm(384, False),
+    "layernorm_1024_drop": lambda: chk_layernorm(1024, True),
+    "layernorm_1536": lambda: chk_layernorm(1536, False),
+    "channel_ln_48": lambda: chk_channel_ln(48),
+    "channel_ln_1024": lambda: chk_channel_ln(1024),
+    "upsample_19_37": lambda: chk_upsample(19, 37),
+    "upsample_37_74": lambda: chk_upsample(37, 74),
+    "patch_gather": chk_patch_gather,
+    "im2col_s2": chk_im2col,
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--one")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "gpu_check.json"))
+    a = ap.parse_args()
+    if a.one:
+        try:
+            r = CHECKS[a.one]()
+        except Exception as e:  # noqa: BLE001
+            r = {"ok": False, "exception": repr(e)[:500]}
+            try:
+                _, L, _ = _imports()
+                r["device_error"] = [hex(v) for v in L.device_error()]
+            except Exception:  # noqa: BLE001
+                pass
+        print("RESULT " + json.dumps(r))
+        return
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    results = {}
+    names = [n for n in CHECKS if a.only in n]
+    for n in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True, text=True,
+                               timeout=180)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            r = json.loads(line[-1][7:]) if line else {"ok": False, "rc": p.returncode, "stderr": p.stderr[-800:]}
+        except subprocess.TimeoutExpired:
+            r = {"ok": False, "timeout": True}
+        r["sec"] = round(time.time() - t0, 1)
+        results[n] = r
+        print(n, json.dumps(r), flush=True)
+        with open(a.out, "w") as f:
+            json.dump(results, f, indent=1)
+    nok = sum(1 for r in results.values() if r.get("ok"))
+    print(f"SUMMARY {nok}/{len(results)} ok")
+
+
+if __name__ == "__main__":
+    main()
