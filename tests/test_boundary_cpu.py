@@ -1,0 +1,102 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol of include/amodal_b200.h,
+and the Python model class keeps the reference's construction / state-dict / error contract.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import amodal_depth_anything_b200 as pkg
+from amodal_depth_anything_b200 import _lib as L
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "amodal_b200.h")).read()
+    declared = set(re.findall(r"\b(ada_[A-Za-z0-9_]+)\s*\(", hdr))
+    declared -= {"ada_model"}
+    assert declared, "no declarations parsed"
+    lib = L.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(L.SIGNATURES), (declared ^ set(L.SIGNATURES))
+
+
+def test_no_cpu_fallback_in_c_abi():
+    """On a box without a GPU every compute entry point must fail loudly (ADA_ENODEVICE), never compute on the host."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = L.load()
+    rc = lib.ada_op_layernorm(None, None, None, None, 1, 384, 1e-6, 1, 0, None)
+    assert rc == L.ADA_ENODEVICE
+    assert b"CUDA" in lib.ada_last_error() or b"device" in lib.ada_last_error()
+
+
+@pytest.mark.parametrize("enc,gt", [("vits", "mask+observation"), ("vitb", "image+mask+observation"), ("vits", "none")])
+def test_state_dict_keys_match_reference_template(enc, gt):
+    m = pkg.AmodalDAv2(guide_type=gt, encoder=enc, pretrained=False)
+    want = synth.state_dict_shapes(enc, gt)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == dict(want)
+    assert "pixel_mean" not in got  # non-persistent buffers (dav2.py:50-51)
+    m.load_state_dict(synth.make_state_dict(enc, gt, 0), strict=True)
+
+
+def test_guidance_conv_zero_init_and_vitg_supported():
+    m = pkg.AmodalDAv2(guide_type="mask+observation", encoder="vits", pretrained=False)
+    sd = m.state_dict()
+    assert sd["encoder.pretrained.patch_embed_guidance.proj.weight"].abs().max() == 0  # dav2.py:55-61
+    assert sd["encoder.pretrained.blocks.0.ls1.gamma"].min() == 1.0
+    assert len(synth.state_dict_shapes("vitg", "mask+observation")) == 649
+    assert pkg.MODEL_CONFIGS["vitg"]["features"] == 384
+
+
+def test_error_conventions():
+    with pytest.raises(KeyError):
+        pkg.AmodalDAv2(encoder="vitx")
+    with pytest.raises(NotImplementedError):
+        pkg.AmodalDAv2(encoder="vits", guide_type="bogus")
+    m = pkg.get_model("AmodalDAv2", guide_type="mask+observation", encoder="vits", pretrained=False)
+    x = torch.rand(1, 3, 28, 28)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m.train()(x, guide_mask=x[:, :1], observation=x[:, :1])
+    m.eval()
+    with pytest.raises(TypeError):
+        m(x, guide_mask=None, observation=x[:, :1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, guide_mask=x[:, :1], observation=x[:, :1])
+    with pytest.raises(KeyError):
+        pkg.get_model("ADDeepLab")
+
+
+def test_save_and_from_pretrained_roundtrip(tmp_path):
+    m = pkg.AmodalDAv2(guide_type="mask", loss_stategy="ssi", encoder="vits", pretrained=False)
+    m.load_state_dict(synth.make_state_dict("vits", "mask", 3), strict=True)
+    m.save_pretrained(tmp_path)
+    assert (tmp_path / "model.safetensors").exists() and (tmp_path / "config.json").exists()
+    m2 = pkg.AmodalDAv2.from_pretrained(str(tmp_path), strict=True)
+    assert m2.guide_type == "mask" and m2.loss_stategy == "ssi" and m2.encoder_name == "vits"
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_pos_embed_interpolation_host_matches_reference_formula():
+    """ada_interp_pos_embed_host runs on the CPU inside the .so; compare with the oracle's interpolate_pos_encoding
+    (dinov2.py:199-230: bicubic with scale_factor=(h+0.1)/37, NOT size=) incl. a non-square grid."""
+    from oracle.amodal_oracle import interpolate_pos_encoding
+    lib = L.load()
+    D = 16
+    g = torch.Generator().manual_seed(0)
+    pos = torch.randn(1, 1 + 37 * 37, D, generator=g)
+    for gh, gw in [(74, 74), (9, 7), (5, 5), (40, 37)]:
+        ref = interpolate_pos_encoding(pos, gh * gw, gh * 14, gw * 14)[0, 1:]
+        src = pos[0, 1:].contiguous()
+        out = torch.empty(gh * gw, D)
+        rc = lib.ada_interp_pos_embed_host(ctypes.c_void_p(src.data_ptr()), 37, D, gh, gw, 0.1, ctypes.c_void_p(out.data_ptr()))
+        assert rc == 0
+        assert (out - ref).abs().max().item() < 1e-4, (gh, gw)  # N(0,1) table; size= variant would differ by ~0.4
