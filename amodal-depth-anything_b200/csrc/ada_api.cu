@@ -128,6 +128,34 @@ struct GemmLaunch {
 
 static int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
 
+// ---- optional per-launch CUDA-event profiler (bench.py's roofline / breakdown; off in the headline timing loop)
+enum ProfClass : int { PC_GEMM_LINEAR = 0, PC_GEMM_CONV, PC_ATTENTION, PC_LAYERNORM, PC_CHANNEL_LN, PC_UPSAMPLE, PC_GATHER, PC_COUNT };
+struct ProfRec {
+  int cls;
+  double flops, bytes;
+  cudaEvent_t a, b;
+};
+struct Profiler {
+  std::vector<ProfRec> recs;
+};
+static Profiler* g_prof = nullptr;
+struct ProfScope {
+  ProfRec* r = nullptr;
+  cudaStream_t st;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+    if (!g_prof) return;
+    ProfRec rec{cls, flops, bytes, nullptr, nullptr};
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    g_prof->recs.push_back(rec);
+    r = &g_prof->recs.back();
+    cudaEventRecord(r->a, st);
+  }
+  ~ProfScope() {
+    if (r) cudaEventRecord(r->b, st);
+  }
+};
+
 static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   GemmArgs g = L.args;
   g.M = L.M;
@@ -167,6 +195,9 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
                     static_cast<uint32_t>(bn));
   const int tiles_n = (L.N + bn - 1) / bn;
   const int num_tiles = tiles_m * tiles_n;
+  const double kreal = (L.a_mode == A_CONV3X3) ? 9.0 * L.Cin : static_cast<double>(L.K);
+  ProfScope prof(L.a_mode == A_CONV3X3 ? PC_GEMM_CONV : PC_GEMM_LINEAR, 2.0 * L.M * static_cast<double>(L.N) * kreal,
+                 2.0 * (static_cast<double>(L.M) * kreal + static_cast<double>(L.N) * kreal + static_cast<double>(L.M) * L.N), st);
   switch (bn) {
     case 32: launch_gemm_bn<32>(ta, tb, g, num_tiles, st); break;
     case 64: launch_gemm_bn<64>(ta, tb, g, num_tiles, st); break;
@@ -180,6 +211,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
 static void launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* out, int rows, int D,
                              float eps, int n_tok, int drop_cls, cudaStream_t st) {
   const int grid = (rows + 7) / 8;
+  ProfScope prof(PC_LAYERNORM, 0.0, 6.0 * rows * static_cast<double>(D), st);
   switch (D / 128) {
     case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
     case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
@@ -212,6 +244,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.out = out;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
+  ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
   attention_tcgen05_kernel<<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, a);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -221,6 +254,7 @@ static void launch_channel_ln_relu(const __nv_bfloat16* in, const float* w, cons
                                    long long pixels, int C, float eps, cudaStream_t st) {
   ADA_REQUIRE(C % 8 == 0 && C <= 1536, "channel LN: C % 8 == 0 and C <= 1536");
   const int grid = static_cast<int>((pixels + 7) / 8);
+  ProfScope prof(PC_CHANNEL_LN, 0.0, 4.0 * pixels * static_cast<double>(C), st);
   if (C <= 512)
     channel_ln_relu_kernel<2><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
   else
@@ -233,6 +267,7 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
                             cudaStream_t st) {
   ADA_REQUIRE(C % 8 == 0, "upsample: C % 8");
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  ProfScope prof(PC_UPSAMPLE, 0.0, 2.0 * B * C * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
   upsample_bilinear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, Hi, Wi, Ho, Wo, C);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -253,6 +288,7 @@ static void launch_patch_gather(const float* rgb, const float* const* guides, co
   src.n = n_guides + 1;
   ADA_REQUIRE(C * 196 <= Kpad, "patch gather: Kpad too small");
   const long long total = static_cast<long long>(B) * (H / 14) * C * 14 * (W / 14);
+  ProfScope prof(PC_GATHER, 0.0, 6.0 * B * C * static_cast<double>(H) * W, st);
   patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
       src, out, B, C, H, W, Kpad, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
   ADA_CHECK_CUDA(cudaGetLastError());
@@ -262,6 +298,7 @@ static void launch_patch_gather(const float* rgb, const float* const* guides, co
 static void launch_im2col_s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
+  ProfScope prof(PC_GATHER, 0.0, 4.0 * total * 8, st);
   im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, H, W, C, Ho, Wo);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -366,11 +403,15 @@ struct RefineW {
 
 using namespace ada;
 
+struct ada_model;
+namespace ada { struct Profiler; }
 struct ada_model {
   ada_config cfg{};
   std::unordered_map<std::string, HostTensor> host;  // raw fp32 state dict (released after finalize)
   bool finalized = false;
   bool capture = false;
+  bool profile = false;
+  ada::Profiler prof;
   std::vector<void*> owned;  // device allocations holding packed weights
 
   // packed weights
@@ -761,6 +802,10 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
   ensure_workspace(m, B, H, W);
   ada_model::PosCache& pc = get_pos(m, gh, gw);
   g_launches = 0;
+  struct ProfGuard {
+    ProfGuard(Profiler* p) { g_prof = p; }
+    ~ProfGuard() { g_prof = nullptr; }
+  } prof_guard(m->profile ? &m->prof : nullptr);
 
   // ---- tokens: patch gather -> embed GEMM (+bias +pos) ; cls rows     (dav2.py:65-76, dinov2.py:232-246)
   launch_patch_gather(rgb, guides, guide_ch, n_guides, m->a_embed, B, H, W, m->kpad, st);
@@ -1065,6 +1110,31 @@ int ada_read_intermediate(ada_handle h, const char* name, float* dst, int64_t co
       ADA_CHECK_CUDA(cudaMemcpy(dst, tmp, count * 4, cudaMemcpyDeviceToHost));
       cudaFree(tmp);
     }
+  });
+}
+
+int ada_set_profile(ada_handle h, int32_t on) {
+  if (!h) return ADA_EINVAL;
+  h->profile = on != 0;
+  return ADA_OK;
+}
+
+int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches) {
+  return guarded([&] {
+    ADA_REQUIRE(h && ms && flops && bytes && launches && n_classes >= PC_COUNT, "bad argument");
+    for (int i = 0; i < n_classes; ++i) ms[i] = flops[i] = bytes[i] = 0.0, launches[i] = 0;
+    ADA_CHECK_CUDA(cudaDeviceSynchronize());
+    for (ProfRec& r : h->prof.recs) {
+      float t = 0.f;
+      ADA_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      ms[r.cls] += t;
+      flops[r.cls] += r.flops;
+      bytes[r.cls] += r.bytes;
+      launches[r.cls] += 1;
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    h->prof.recs.clear();
   });
 }
 

@@ -68,6 +68,12 @@ int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W);
  * "path_1".."path_4" (NHWC), "tokens" (x after prepare_tokens_with_masks; needs ada_set_capture(h,1)). */
 int ada_read_intermediate(ada_handle h, const char* name, float* dst, int64_t count);
 int ada_set_capture(ada_handle h, int32_t on);
+/* Measurement hook (bench.py): when on, every kernel launch of ada_forward is bracketed by CUDA events on the launch
+ * stream. ada_profile_read syncs, then sums per kernel class since the last read: elapsed ms, algorithmic FLOPs,
+ * algorithmic bytes, launches. Classes: 0 tcgen05 GEMM (linear), 1 tcgen05 GEMM (implicit conv3x3), 2 attention,
+ * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls / im2col). n_classes >= 7. */
+int ada_set_profile(ada_handle h, int32_t on);
+int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches);
 void ada_destroy(ada_handle h);
 const char* ada_last_error(void);
 /* Device error mailbox written by a kernel that timed out on a barrier (4 words: code, block, parity, thread). */
