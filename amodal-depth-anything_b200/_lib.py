@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libamodal_b200.so")
 ADA_OK, ADA_EINVAL, ADA_ENODEVICE, ADA_ECUDA, ADA_ESTATE = 0, -1, -2, -3, -4
 
 # epilogue / activation / A-operand modes (csrc/gemm.cuh)
-EPI_BF16, EPI_RESID_F32, EPI_EMBED, EPI_CONVT, EPI_TAIL, EPI_SWIGLU = range(6)
+EPI_BF16, _EPI_UNUSED, EPI_EMBED, EPI_CONVT, EPI_TAIL, EPI_SWIGLU = range(6)
 ACT_NONE, ACT_GELU, ACT_RELU = range(3)
 A_LINEAR, A_CONV3X3 = range(2)
 
@@ -85,13 +85,14 @@ SIGNATURES = {
     "ada_set_profile": (c_int32, [c_void_p, c_int32]),
     "ada_profile_read": (c_int32, [c_void_p, c_int32, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                    POINTER(ctypes.c_double), POINTER(c_int32)]),
+    "ada_profile_records": (c_int32, [c_void_p, c_int32, POINTER(c_int32), POINTER(ctypes.c_double)]),
     "ada_destroy": (None, [c_void_p]),
     "ada_last_error": (c_char_p, []),
     "ada_device_error": (c_int32, [POINTER(c_uint32 * 4)]),
     "ada_interp_pos_embed_host": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "ada_op_gemm": (c_int32, [POINTER(GemmDesc), c_void_p]),
-    "ada_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_int32,
-                                   c_void_p]),
+    "ada_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32,
+                                   c_int32, c_int32, c_void_p]),
     "ada_op_attention": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "ada_op_channel_ln_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "ada_op_upsample": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -88,8 +88,8 @@ static void require_device() {
 
 // ------------------------------------------------------------------------------------------------ GEMM launcher
 template <int BN>
-static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int num_tiles,
-                           cudaStream_t st) {
+static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+                           const GemmArgs& g, int num_tiles, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -98,14 +98,14 @@ static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const G
     attr_set = true;
   }
   const int grid = std::min(num_tiles, device_info().sms);
-  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, g);
+  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, tc2, g);
   ADA_CHECK_CUDA(cudaGetLastError());
 }
 
 static int pick_bn(int N) {
   // smallest padded N wins; ties go to the wider tile (fewer A re-reads, better smem operand bandwidth)
-  int best = 32, best_pad = round_up(N, 32);
-  const int cands[3] = {64, 128, 256};
+  int best = 64, best_pad = round_up(N, 64);  // 32 is reserved for the fused tail (EPI_TAIL)
+  const int cands[2] = {128, 256};
   for (int c : cands) {
     const int pad = round_up(N, c);
     if (pad <= best_pad + best_pad / 16) {  // allow ~6% padding for a wider tile
@@ -123,6 +123,7 @@ struct GemmLaunch {
   int a_mode = A_LINEAR;
   int batch = 0, H = 0, W = 0, Cin = 0;
   GemmArgs args{};           // epilogue fields filled by caller
+  __nv_bfloat16* out_relu = nullptr;  // EPI_BF16: optional relu(out) copy (second TMA store map)
   int force_bn = 0;
 };
 
@@ -134,6 +135,7 @@ struct ProfRec {
   int cls;
   double flops, bytes;
   cudaEvent_t a, b;
+  int m, n, k, tag;  // shape + (epi | act << 4 | bn << 8) for GEMMs
 };
 struct Profiler {
   std::vector<ProfRec> recs;
@@ -144,7 +146,7 @@ struct ProfScope {
   cudaStream_t st;
   ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
     if (!g_prof) return;
-    ProfRec rec{cls, flops, bytes, nullptr, nullptr};
+    ProfRec rec{cls, flops, bytes, nullptr, nullptr, 0, 0, 0, 0};
     cudaEventCreate(&rec.a);
     cudaEventCreate(&rec.b);
     g_prof->recs.push_back(rec);
@@ -164,8 +166,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   g.a_mode = L.a_mode;
   int bn = L.force_bn ? L.force_bn : pick_bn(g.epi == EPI_SWIGLU ? std::max(L.N, 64) : L.N);
   if (g.epi == EPI_TAIL) bn = 32;
-  if (g.epi == EPI_SWIGLU && bn < 64) bn = 64;
+  if (g.epi == EPI_SWIGLU && bn < 128) bn = 128;
   ADA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "bad BN");
+  ADA_REQUIRE(bn != 32 || g.epi == EPI_TAIL, "BN=32 is only built for the fused tail epilogue");
+  ADA_REQUIRE(g.epi != EPI_SWIGLU || L.N % 128 == 0, "SwiGLU needs N % 128 == 0");
   ADA_REQUIRE(L.ldb % 8 == 0, "weight pitch must be a multiple of 8 elements");
   CUtensorMap ta, tb;
   int tiles_m;
@@ -193,30 +197,60 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   }
   tb = make_tmap_2d(L.Bw, static_cast<uint64_t>(g.K), static_cast<uint64_t>(L.N), static_cast<uint64_t>(L.ldb), kBlockK,
                     static_cast<uint32_t>(bn));
+  // output maps for the TMA-store epilogues (dummy = tb otherwise; never dereferenced)
+  CUtensorMap tc = tb, tc2 = tb;
+  g.has_relu_copy = 0;
+  if (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU) {
+    const int n_out = (g.epi == EPI_SWIGLU) ? L.N / 2 : L.N;
+    ADA_REQUIRE(g.out_bf16 != nullptr && g.ldo % 8 == 0 && n_out % 8 == 0, "bf16 output needs ldo, N multiples of 8");
+    auto make_c = [&](const void* ptr) {
+      if (L.a_mode == A_CONV3X3) {
+        ADA_REQUIRE(g.ldo == n_out, "conv output must be dense NHWC");
+        uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(L.W), static_cast<uint64_t>(L.H),
+                            static_cast<uint64_t>(L.batch)};
+        uint64_t str[3] = {static_cast<uint64_t>(n_out) * 2, static_cast<uint64_t>(L.W) * n_out * 2,
+                           static_cast<uint64_t>(L.H) * L.W * n_out * 2};
+        uint32_t box[4] = {64, kTileW, 2, 1};
+        return make_tmap_bf16(ptr, 4, dims, str, box);
+      }
+      return make_tmap_2d(ptr, static_cast<uint64_t>(n_out), static_cast<uint64_t>(L.M), static_cast<uint64_t>(g.ldo), 64, 32);
+    };
+    tc = make_c(g.out_bf16);
+    if (L.out_relu) {
+      tc2 = make_c(L.out_relu);
+      g.has_relu_copy = 1;
+    }
+  }
   const int tiles_n = (L.N + bn - 1) / bn;
   const int num_tiles = tiles_m * tiles_n;
   const double kreal = (L.a_mode == A_CONV3X3) ? 9.0 * L.Cin : static_cast<double>(L.K);
   ProfScope prof(L.a_mode == A_CONV3X3 ? PC_GEMM_CONV : PC_GEMM_LINEAR, 2.0 * L.M * static_cast<double>(L.N) * kreal,
                  2.0 * (static_cast<double>(L.M) * kreal + static_cast<double>(L.N) * kreal + static_cast<double>(L.M) * L.N), st);
+  if (prof.r) {
+    prof.r->m = L.M;
+    prof.r->n = L.N;
+    prof.r->k = static_cast<int>(kreal);
+    prof.r->tag = g.epi | (g.act << 4) | (bn << 8);
+  }
   switch (bn) {
-    case 32: launch_gemm_bn<32>(ta, tb, g, num_tiles, st); break;
-    case 64: launch_gemm_bn<64>(ta, tb, g, num_tiles, st); break;
-    case 128: launch_gemm_bn<128>(ta, tb, g, num_tiles, st); break;
-    default: launch_gemm_bn<256>(ta, tb, g, num_tiles, st); break;
+    case 32: launch_gemm_bn<32>(ta, tb, tc, tc2, g, num_tiles, st); break;
+    case 64: launch_gemm_bn<64>(ta, tb, tc, tc2, g, num_tiles, st); break;
+    case 128: launch_gemm_bn<128>(ta, tb, tc, tc2, g, num_tiles, st); break;
+    default: launch_gemm_bn<256>(ta, tb, tc, tc2, g, num_tiles, st); break;
   }
   ++g_launches;
 }
 
 // ------------------------------------------------------------------------------------------------ other launchers
-static void launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* out, int rows, int D,
-                             float eps, int n_tok, int drop_cls, cudaStream_t st) {
+static void launch_layernorm(float* x, const __nv_bfloat16* delta, const float* w, const float* b, __nv_bfloat16* out,
+                             int rows, int D, float eps, int n_tok, int drop_cls, int write_x, cudaStream_t st) {
   const int grid = (rows + 7) / 8;
-  ProfScope prof(PC_LAYERNORM, 0.0, 6.0 * rows * static_cast<double>(D), st);
+  ProfScope prof(PC_LAYERNORM, 0.0, (6.0 + (delta ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0)) * rows * static_cast<double>(D), st);
   switch (D / 128) {
-    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
-    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
-    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
-    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, w, b, out, rows, eps, n_tok, drop_cls); break;
+    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
     default: throw AdaError(ADA_EINVAL, "layernorm: embed_dim must be 384/768/1024/1536");
   }
   ADA_REQUIRE(D % 128 == 0, "layernorm: D % 128");
@@ -447,7 +481,7 @@ struct ada_model {
   std::unordered_map<std::string, int> named_is_f32;
   // buffers
   float* x = nullptr;
-  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *a_embed = nullptr;
+  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *ybuf = nullptr, *a_embed = nullptr;
   __nv_bfloat16* tap[4] = {};
   float* tokens_dbg = nullptr;
   __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *col4 = nullptr, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
@@ -685,6 +719,7 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
   m->qkv = b.take<__nv_bfloat16>(M * 3 * D);
   m->att = b.take<__nv_bfloat16>(M * D);
   m->hbuf = b.take<__nv_bfloat16>(M * c.ffn_hidden);
+  m->ybuf = b.take<__nv_bfloat16>(M * D);
   m->a_embed = b.take<__nv_bfloat16>(BP * m->kpad);
   m->tokens_dbg = b.take<float>(M * D);
   reg("tokens", m->tokens_dbg, M * D, 1);
@@ -766,7 +801,7 @@ static void conv3x3(const __nv_bfloat16* in, int B, int H, int W, const ConvW& c
   L.args.resid1 = r1;
   L.args.resid2 = r2;
   L.args.out_bf16 = out;
-  L.args.out_relu = out_relu;
+  L.out_relu = out_relu;
   L.args.ldo = cw.cout;
   launch_gemm(L, st);
 }
@@ -824,11 +859,14 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
   if (m->capture)
     ADA_CHECK_CUDA(cudaMemcpyAsync(m->tokens_dbg, m->x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, st));
 
-  // ---- encoder blocks (block.py:82-107 eval branch)
+  // ---- encoder blocks (block.py:82-107 eval branch). The fp32 stream x is only touched by the LayerNorm kernel:
+  //      each residual branch leaves gamma * (W h + b) in `ybuf` (bf16) and the NEXT LayerNorm folds it in
+  //      (x <- x + ybuf, block.py:105-106) before normalising.
   int tap_i = 0;
+  const __nv_bfloat16* pending = nullptr;  // residual-branch output not yet added to x
   for (int i = 0; i < c.depth; ++i) {
     const BlockW& w = m->blocks[i];
-    launch_layernorm(m->x, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, st);
+    launch_layernorm(m->x, pending, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 1, st);
     {
       GemmArgs e{};
       e.epi = EPI_BF16;
@@ -840,15 +878,14 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
     launch_attention(m->qkv, m->att, B, N, heads, st);
     {
       GemmArgs e{};
-      e.epi = EPI_RESID_F32;
+      e.epi = EPI_BF16;
       e.bias = w.bproj;
       e.gamma = w.g1;
-      e.resid_f32 = m->x;
-      e.out_f32 = m->x;
+      e.out_bf16 = m->ybuf;
       e.ldo = D;
       linear(m->att, M, D, D, w.wproj, D, D, e, st);
     }
-    launch_layernorm(m->x, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, st);
+    launch_layernorm(m->x, m->ybuf, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 1, st);
     const int Hd = c.ffn_hidden;
     {
       GemmArgs e{};
@@ -866,16 +903,18 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
     }
     {
       GemmArgs e{};
-      e.epi = EPI_RESID_F32;
+      e.epi = EPI_BF16;
       e.bias = w.b2;
       e.gamma = w.g2;
-      e.resid_f32 = m->x;
-      e.out_f32 = m->x;
+      e.out_bf16 = m->ybuf;
       e.ldo = D;
       linear(m->hbuf, M, Hd, Hd, w.w2, D, Hd, e, st);
     }
-    if (tap_i < 4 && i == c.taps[tap_i]) {  // shared final norm, cls dropped, NHWC patch map (dinov2.py:337-340)
-      launch_layernorm(m->x, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, st);
+    pending = m->ybuf;
+    if (tap_i < 4 && i == c.taps[tap_i]) {
+      // shared final norm of (x + pending), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is updated by
+      // the next block's first LayerNorm, so nothing is written back here
+      launch_layernorm(m->x, pending, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
       ++tap_i;
     }
   }
@@ -1119,6 +1158,25 @@ int ada_set_profile(ada_handle h, int32_t on) {
   return ADA_OK;
 }
 
+int ada_profile_records(ada_handle h, int32_t max_recs, int32_t* meta, double* ms) {
+  if (!h || !meta || !ms) return ADA_EINVAL;
+  if (cudaDeviceSynchronize() != cudaSuccess) return ADA_ECUDA;
+  int n = 0;
+  for (ProfRec& r : h->prof.recs) {
+    if (n >= max_recs) break;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return ADA_ECUDA;
+    meta[5 * n + 0] = r.cls;
+    meta[5 * n + 1] = r.m;
+    meta[5 * n + 2] = r.n;
+    meta[5 * n + 3] = r.k;
+    meta[5 * n + 4] = r.tag;
+    ms[n] = t;
+    ++n;
+  }
+  return n;
+}
+
 int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches) {
   return guarded([&] {
     ADA_REQUIRE(h && ms && flops && bytes && launches && n_classes >= PC_COUNT, "bad argument");
@@ -1172,10 +1230,9 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     e.act = d->act;
     e.bias = d->bias;
     e.gamma = d->gamma;
-    e.resid_f32 = d->resid_f32;
     e.out_f32 = d->out_f32;
     e.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
-    e.out_relu = static_cast<__nv_bfloat16*>(d->out_relu);
+    L.out_relu = static_cast<__nv_bfloat16*>(d->out_relu);
     e.resid1 = static_cast<const __nv_bfloat16*>(d->resid1);
     e.resid2 = static_cast<const __nv_bfloat16*>(d->resid2);
     e.aux = d->aux;
@@ -1192,12 +1249,12 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
   });
 }
 
-int ada_op_layernorm(const float* x, const float* w, const float* b, void* out_bf16, int32_t rows, int32_t D, float eps,
-                     int32_t n_tok, int32_t drop_cls, void* stream) {
+int ada_op_layernorm(float* x, const void* delta_bf16, const float* w, const float* b, void* out_bf16, int32_t rows,
+                     int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x, void* stream) {
   return guarded([&] {
     require_device();
-    launch_layernorm(x, w, b, static_cast<__nv_bfloat16*>(out_bf16), rows, D, eps, n_tok, drop_cls,
-                     static_cast<cudaStream_t>(stream));
+    launch_layernorm(x, static_cast<const __nv_bfloat16*>(delta_bf16), w, b, static_cast<__nv_bfloat16*>(out_bf16), rows, D,
+                     eps, n_tok, drop_cls, write_x, static_cast<cudaStream_t>(stream));
   });
 }
 

@@ -16,10 +16,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reference: nn.LayerNorm(D, eps=1e-6) block.py:84,87 and the shared final norm dinov2.py:337-338.
 // drop_cls != 0: input rows are [B, n_tok, D]; token 0 (cls) is skipped and the output is the dense patch map
 // [B, n_tok-1, D] == NHWC [B, h, w, D] (dinov2.py:339-340 + dpt.py:168-171 collapse into the store address).
+// delta != nullptr: the pending residual-branch output (bf16, already LayerScale'd by the GEMM epilogue) is added
+// first, x <- x + delta (block.py:105-106), and written back when write_x is set; the fp32 stream is therefore only
+// ever touched by this coalesced kernel, never by the (row-per-thread) GEMM epilogue.
 template <int CHUNKS>  // D = CHUNKS * 128
 __global__ void __launch_bounds__(256)
-layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                      __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls) {
+layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const float* __restrict__ w,
+                      const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok,
+                      int drop_cls, int write_x) {
   constexpr int D = CHUNKS * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -30,14 +34,25 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     if (t == 0) return;
     orow = static_cast<long long>(bi) * (n_tok - 1) + (t - 1);
   }
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<long long>(row) * D);
   float4 v[CHUNKS];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < CHUNKS; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < CHUNKS; ++i) v[i] = xr[lane + 32 * i];
+  if (delta != nullptr) {
+    const uint2* dr = reinterpret_cast<const uint2*>(delta + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const uint2 d = dr[lane + 32 * i];
+      v[i].x += bf16_lo(d.x); v[i].y += bf16_hi(d.x); v[i].z += bf16_lo(d.y); v[i].w += bf16_hi(d.y);
+    }
+    if (write_x) {
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) xr[lane + 32 * i] = v[i];
+    }
   }
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll

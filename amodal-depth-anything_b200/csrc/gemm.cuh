@@ -3,14 +3,20 @@
 //   warp 0      : TMA producer  (A and B tiles, 128-byte swizzle, 4..8 stage mbarrier ring)
 //   warp 1      : MMA issuer    (tcgen05.mma cta_group::1, 128 x BN x 16, fp32 accumulators in TMEM, 2 accumulator stages)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem -> TMA store)
 //
 // The A operand is fetched either as a plain row-major matrix (linear layers, 1x1 convs, transposed convs with k == s)
 // or as an implicit-GEMM 3x3/pad-1/stride-1 convolution over an NHWC map: the M tile is an 8x16 pixel patch and each
 // of the 9 taps is one shifted 4-D TMA box whose out-of-bounds part the hardware zero-fills (that is the padding).
 //
+// Epilogue data path. After tcgen05.ld each thread owns one accumulator row; storing that straight to global touches
+// 32 different cache lines per warp instruction (measured: 32 sectors/request, K=1024 GEMMs ran epilogue-bound at
+// ~45% of the K=4096 rate). Instead every epilogue warp converts 64 columns at a time, writes its 32x64 bf16 block
+// into a private 4 KB swizzled staging buffer (conflict-free 16-byte stores) and one lane issues a TMA store; the
+// hardware clips rows/columns/pixels that fall outside the tensor, so ragged M, N, H, W need no predication.
+//
 // Reference ops this kernel replaces (all fp32 torch ops in the reference):
-//   attention.py:51,60  mlp.py:36-39  swiglu_ffn.py:30-33  layer_scale.py:28  block.py:105-106   (encoder linears)
+//   attention.py:51,60  mlp.py:36-39  swiglu_ffn.py:30-33  layer_scale.py:28                     (encoder linears)
 //   patch_embed.py:76   dinov2.py:234-246                                                       (patch embed + pos)
 //   dpt.py:172-173,178  blocks.py:20-24,57-80,146  dpt.py:193,195                                (DPT head convs)
 #pragma once
@@ -26,12 +32,11 @@ constexpr int kTileW = 16;
 constexpr int kGemmThreads = 256;
 
 enum EpiMode : int {
-  EPI_BF16 = 0,       // out_bf16 = act(acc + bias) [+ resid1 + resid2]; optional second copy with ReLU applied
-  EPI_RESID_F32 = 1,  // out_f32 = resid_f32 + gamma * (acc + bias)          (LayerScale + residual, fp32 stream)
+  EPI_BF16 = 0,       // out_bf16 = act((acc + bias) * gamma) [+ resid1 + resid2]; optional second copy with ReLU; TMA store
   EPI_EMBED = 2,      // out_f32[b*(P+1)+1+p, :] = acc + aux[p, :]           (patch embed: + bias + pos-embed, skip cls row)
   EPI_CONVT = 3,      // k == s transposed conv: pixel-shuffle scatter, + bias[co]
   EPI_TAIL = 4,       // sigmoid(relu(acc + bias) . aux[0:32] + aux[32]) -> fp32 per pixel (BN must be 32)
-  EPI_SWIGLU = 5      // columns interleaved in 32-wide (x1, x2) chunk pairs: out = silu(x1 + b1) * (x2 + b2)
+  EPI_SWIGLU = 5      // columns interleaved in 32-wide (x1, x2) chunk pairs: out = silu(x1 + b1) * (x2 + b2); TMA store
 };
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1 };
@@ -44,11 +49,9 @@ struct GemmArgs {
   int H, W, tiles_x, tiles_y, c_chunks;  // c_chunks = c_pad / 64
   // epilogue operands
   const float* bias;        // [N] (EPI_CONVT: [Cout]) or nullptr
-  const float* gamma;       // [N]
-  const float* resid_f32;   // may alias out_f32
+  const float* gamma;       // [N] LayerScale, or nullptr
   float* out_f32;
-  __nv_bfloat16* out_bf16;
-  __nv_bfloat16* out_relu;  // optional relu(out) copy
+  __nv_bfloat16* out_bf16;  // direct-store modes only (EPI_CONVT); TMA-store modes use tmap_c
   const __nv_bfloat16* resid1;
   const __nv_bfloat16* resid2;
   const float* aux;
@@ -56,6 +59,7 @@ struct GemmArgs {
   int P;                    // EPI_EMBED: patches per image
   int ks, cout;             // EPI_CONVT: kernel == stride, output channels
   int sigmoid;              // EPI_TAIL
+  int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
 };
 
 template <int BN>
@@ -66,20 +70,50 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
+  static constexpr int kStagingBytes = 4 * 2 * 4096;             // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int kVecBytes = 2 * 256 * 4;                  // bias + gamma of the current N tile
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KB alignment
+  // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1 KB aligned (checked)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + kBarBytes;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, mlp.py:30-41). erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
+// bf16 rounding of the stored activation): 2 MUFU ops + ~12 FMAs instead of erff's branchy ~40 instructions.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = fast_exp2(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4 rr) {
+  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  uint8_t* smem_gen = smem_raw;
+  if (threadIdx.x == 0 && (smem_base & 1023u)) {  // swizzled tiles need a 1 KB aligned window
+    g_dev_error[0] = 0xA10;
+    __trap();
+  }
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;  // 1 KB aligned (stage sizes are)
+  const uint32_t vec_off = Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes;
+  float* s_vec = reinterpret_cast<float*>(smem_gen + vec_off);  // [bias 256 | gamma 256]
+  const uint32_t bar_base = smem_base + vec_off + Cfg::kVecBytes;
   // barrier layout: full[kStages], empty[kStages], tfull[2], tempty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
@@ -93,6 +127,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -187,8 +222,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // accumulator row owned by this thread
+    const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
+    const uint32_t stg0 = staging_base + static_cast<uint32_t>(q) * 8192u;  // this warp's two 4 KB staging buffers
+    const uint32_t st_row = static_cast<uint32_t>(lane) * 128u;
+    const uint32_t st_sw = static_cast<uint32_t>(lane & 7);
+    int sbuf = 0;                      // staging buffer to use next
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool tma_out = (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / tiles_n, nt = t % tiles_n;
       const int n0 = nt * BN;
@@ -196,12 +237,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       bool valid;
       long long orow;  // output row index (pixels / tokens)
       int m;           // logical A row (used by EMBED / CONVT)
+      int img = 0, y0 = 0, x0 = 0;
       if (g.a_mode == A_CONV3X3) {
         const int per_img = g.tiles_x * g.tiles_y;
-        const int img = mt / per_img;
+        img = mt / per_img;
         const int r = mt % per_img;
-        const int y = (r / g.tiles_x) * kTileH + row / kTileW;
-        const int x = (r % g.tiles_x) * kTileW + row % kTileW;
+        y0 = (r / g.tiles_x) * kTileH;
+        x0 = (r % g.tiles_x) * kTileW;
+        const int y = y0 + row / kTileW;
+        const int x = x0 + row % kTileW;
         valid = (y < g.H) && (x < g.W);
         orow = (static_cast<long long>(img) * g.H + y) * g.W + x;
         m = static_cast<int>(orow);
@@ -215,11 +259,118 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         orow = static_cast<long long>(b) * (g.P + 1) + 1 + p;
       }
 
+      // ---- stage this N tile's bias / gamma in shared memory: barrier (previous tile's readers done) -> write -> barrier
+      float* s_bias = s_vec;
+      float* s_gamma = s_bias + 256;
+      if (tma_out) {
+        named_bar_sync(1, 128);
+        for (int i = et; i < BN; i += 128) {
+          const int n = n0 + i;
+          s_bias[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
+          s_gamma[i] = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
+        }
+        named_bar_sync(1, 128);
+      }
+
       mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      if (g.epi == EPI_TAIL) {
+      if (tma_out) {
+        if constexpr (BN >= 64) {
+          const int out_cols = (g.epi == EPI_SWIGLU) ? BN / 2 : BN;  // output columns produced by this tile
+          const int on0 = (g.epi == EPI_SWIGLU) ? (n0 >> 1) : n0;
+          const int n_out = (g.epi == EPI_SWIGLU) ? (g.N >> 1) : g.N;
+#pragma unroll 1
+          for (int cg = 0; cg < out_cols / 64; ++cg) {
+            const int oc = on0 + cg * 64;  // first output column of this 64-wide group
+            if (oc >= n_out) break;
+            uint32_t pk[32];               // 64 bf16 outputs of this thread's row
+            if (g.epi == EPI_SWIGLU) {
+              // 128 interleaved accumulator columns: [x1 32 | x2 32 | x1 32 | x2 32]
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t a[32], b[32];
+                tmem_ld32(t_addr + cg * 128 + h * 64, a);
+                tmem_ld32(t_addr + cg * 128 + h * 64 + 32, b);
+                tmem_ld_wait();
+                const float* bb = s_bias + cg * 128 + h * 64;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float x1a = __uint_as_float(a[j]) + bb[j], x1b = __uint_as_float(a[j + 1]) + bb[j + 1];
+                  const float x2a = __uint_as_float(b[j]) + bb[32 + j], x2b = __uint_as_float(b[j + 1]) + bb[33 + j];
+                  const float ha = __fdividef(x1a, 1.0f + __expf(-x1a)) * x2a;
+                  const float hb = __fdividef(x1b, 1.0f + __expf(-x1b)) * x2b;
+                  pk[h * 16 + (j >> 1)] = pack_bf16x2(ha, hb);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(t_addr + cg * 64 + h * 32, r);
+                tmem_ld_wait();
+                const float* bb = s_bias + cg * 64 + h * 32;
+                const float* gg = s_gamma + cg * 64 + h * 32;
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[gi * 8 + j]) + bb[gi * 8 + j]) * gg[gi * 8 + j];
+                  if (g.act == ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+                  } else if (g.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                  }
+                  if (g.resid1 != nullptr || g.resid2 != nullptr) {
+                    const int n = oc + h * 32 + gi * 8;
+                    if (valid && n < g.N) {
+                      const long long off = orow * g.ldo + n;
+                      if (g.resid1) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid1 + off));
+                      if (g.resid2) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid2 + off));
+                    }
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+                }
+              }
+            }
+            // ---- registers -> swizzled staging buffer -> TMA store
+            const int passes = g.has_relu_copy ? 2 : 1;
+            for (int pass = 0; pass < passes; ++pass) {
+              const uint32_t buf = stg0 + static_cast<uint32_t>(sbuf) * 4096u;
+              if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has drained it
+              __syncwarp();
+              if (pass == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {  // relu on packed bf16 pairs: clear negatives (sign bit set)
+                  uint32_t w = pk[i];
+                  if (w & 0x00008000u) w &= 0xFFFF0000u;
+                  if (w & 0x80000000u) w &= 0x0000FFFFu;
+                  pk[i] = w;
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                st_shared_v4(buf + st_row + ((static_cast<uint32_t>(c) ^ st_sw) << 4), pk[4 * c], pk[4 * c + 1],
+                             pk[4 * c + 2], pk[4 * c + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const CUtensorMap* tm = (pass == 0) ? &tmap_c : &tmap_c2;
+                if (g.a_mode == A_CONV3X3)
+                  tma_store_4d(tm, buf, oc, x0, y0 + 2 * q, img);
+                else
+                  tma_store_2d(tm, buf, oc, mt * kBlockM + q * 32);
+                bulk_commit();
+              }
+              sbuf ^= 1;
+            }
+          }
+        }
+      } else if (g.epi == EPI_TAIL) {
         if constexpr (BN == 32) {
           uint32_t r[32];
           tmem_ld32(t_addr, r);
@@ -234,34 +385,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (g.sigmoid) s = 1.0f / (1.0f + __expf(-s));
           if (valid) g.out_f32[orow] = s;
         }
-      } else if (g.epi == EPI_SWIGLU) {
-        // chunk pairs: even 32-col chunk = x1, odd = x2 (weights were interleaved at pack time)
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint32_t a[32], b[32];
-          tmem_ld32(t_addr + c * 64, a);
-          tmem_ld32(t_addr + c * 64 + 32, b);
-          tmem_ld_wait();
-          const int nb = n0 + c * 64;          // interleaved column of x1 chunk
-          const int on = (n0 >> 1) + c * 32;   // output column
-          if (valid && nb < g.N) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float x1a = __uint_as_float(a[j]) + __ldg(g.bias + nb + j);
-              float x1b = __uint_as_float(a[j + 1]) + __ldg(g.bias + nb + j + 1);
-              float x2a = __uint_as_float(b[j]) + __ldg(g.bias + nb + 32 + j);
-              float x2b = __uint_as_float(b[j + 1]) + __ldg(g.bias + nb + 32 + j + 1);
-              float ha = x1a / (1.0f + __expf(-x1a)) * x2a;
-              float hb = x1b / (1.0f + __expf(-x1b)) * x2b;
-              pk[j >> 1] = pack_bf16x2(ha, hb);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + orow * g.ldo + on);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-          }
-        }
       } else {
+        // EPI_EMBED / EPI_CONVT: direct per-thread stores (one GEMM each per forward; row remap / pixel-shuffle scatter)
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -269,24 +394,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           const int nb = n0 + c * 32;
           if (!valid || nb >= g.N) continue;
-          if (g.epi == EPI_RESID_F32) {
-            const float* rs = g.resid_f32 + orow * g.ldo + nb;
-            float* dst = g.out_f32 + orow * g.ldo + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (nb + j < g.N) {
-                const float4 xr = *reinterpret_cast<const float4*>(rs + j);
-                const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
-                const float4 ga = __ldg(reinterpret_cast<const float4*>(g.gamma + nb + j));
-                float4 o;
-                o.x = fmaf(ga.x, __uint_as_float(r[j]) + bi.x, xr.x);
-                o.y = fmaf(ga.y, __uint_as_float(r[j + 1]) + bi.y, xr.y);
-                o.z = fmaf(ga.z, __uint_as_float(r[j + 2]) + bi.z, xr.z);
-                o.w = fmaf(ga.w, __uint_as_float(r[j + 3]) + bi.w, xr.w);
-                *reinterpret_cast<float4*>(dst + j) = o;
-              }
-            }
-          } else if (g.epi == EPI_EMBED) {
+          if (g.epi == EPI_EMBED) {
             const int p = m % g.P;
             const float* ax = g.aux + static_cast<long long>(p) * g.N + nb;
             float* dst = g.out_f32 + orow * g.ldo + nb;
@@ -303,64 +411,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           } else {
-            // EPI_BF16 / EPI_CONVT: 8-column groups, one 16-byte store each
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
               const int n = nb + gi * 8;
               if (n >= g.N) break;
+              const int kk = n / g.cout, co = n % g.cout;
+              const int ky = kk / g.ks, kx = kk % g.ks;
+              const int hw = g.H * g.W;
+              const int b = m / hw, rem = m % hw;
+              const int y = rem / g.W, x = rem % g.W;
+              const long long off =
+                  ((static_cast<long long>(b) * g.H * g.ks + y * g.ks + ky) * (g.W * g.ks) + x * g.ks + kx) * g.cout + co;
               float v[8];
-              long long off;
-              const float* bptr;
-              if (g.epi == EPI_CONVT) {
-                const int kk = n / g.cout, co = n % g.cout;
-                const int ky = kk / g.ks, kx = kk % g.ks;
-                const int hw = g.H * g.W;
-                const int b = m / hw, rem = m % hw;
-                const int y = rem / g.W, x = rem % g.W;
-                off = ((static_cast<long long>(b) * g.H * g.ks + y * g.ks + ky) * (g.W * g.ks) + x * g.ks + kx) *
-                          g.cout + co;
-                bptr = g.bias ? g.bias + co : nullptr;
-              } else {
-                off = orow * g.ldo + n;
-                bptr = g.bias ? g.bias + n : nullptr;
-              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gi * 8 + j]);
-              if (bptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + 4));
+              if (g.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + co));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + co + 4));
                 v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                 v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
               }
-              if (g.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              } else if (g.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-              }
-              if (g.resid1) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(g.resid1 + off);
-                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-              }
-              if (g.resid2) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(g.resid2 + off);
-                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-              }
-              if (g.out_bf16) {
-                *reinterpret_cast<uint4*>(g.out_bf16 + off) =
-                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                               pack_bf16x2(v[6], v[7]));
-              }
-              if (g.out_relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-                *reinterpret_cast<uint4*>(g.out_relu + off) =
-                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                               pack_bf16x2(v[6], v[7]));
-              }
+              *reinterpret_cast<uint4*>(g.out_bf16 + off) = make_uint4(
+                  pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
           }
         }
@@ -371,6 +443,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) bulk_wait<0>();  // all TMA stores of this warp have completed before the CTA retires
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--detail", default="", help="write per-launch-signature timings of the profile pass to this JSON file")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":
@@ -241,6 +242,25 @@ def main():
         lib.ada_set_profile(model._handle, 1)
         for _ in range(a.profile_steps):
             step()
+        if a.detail and rank == 0:
+            cap = 4096
+            meta, rms = (ctypes.c_int32 * (5 * cap))(), (ctypes.c_double * cap)()
+            nrec = lib.ada_profile_records(model._handle, cap, meta, rms)
+            agg = {}
+            for i in range(max(nrec, 0)):
+                c, m_, n_, k_, tag = meta[5 * i:5 * i + 5]
+                key = f"{PROF_CLASSES[c]} M={m_} N={n_} K={k_} epi={tag & 15} act={(tag >> 4) & 15} bn={tag >> 8}"
+                e = agg.setdefault(key, {"ms": 0.0, "n": 0, "flops": 2.0 * m_ * n_ * k_})
+                e["ms"] += rms[i]
+                e["n"] += 1
+            rows = []
+            for key, e in agg.items():
+                avg = e["ms"] / e["n"]
+                rows.append({"sig": key, "launches": e["n"] // a.profile_steps, "avg_ms": avg,
+                             "ms_per_step": e["ms"] / a.profile_steps,
+                             "tflops": e["flops"] / avg / 1e9 if e["flops"] else None})
+            rows.sort(key=lambda r: -r["ms_per_step"])
+            json.dump(rows, open(a.detail, "w"), indent=1)
         n = len(PROF_CLASSES)
         msv, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
         ln = (ctypes.c_int32 * n)()

@@ -74,6 +74,9 @@ int ada_set_capture(ada_handle h, int32_t on);
  * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls / im2col). n_classes >= 7. */
 int ada_set_profile(ada_handle h, int32_t on);
 int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches);
+/* Raw records since the last ada_profile_read (call before it): meta[5*i..] = class, M, N, K, epi|act<<4|BN<<8; ms[i].
+ * Returns the number of records written (<= max_recs) or a negative error code. */
+int ada_profile_records(ada_handle h, int32_t max_recs, int32_t* meta, double* ms);
 void ada_destroy(ada_handle h);
 const char* ada_last_error(void);
 /* Device error mailbox written by a kernel that timed out on a barrier (4 words: code, block, parity, thread). */
@@ -95,7 +98,7 @@ typedef struct ada_gemm_desc {
   int32_t batch, H, W, Cin;   /* conv mode geometry; EPI_CONVT: input grid */
   const float* bias;
   const float* gamma;
-  const float* resid_f32;
+  const float* resid_f32; /* unused (kept for layout stability) */
   float* out_f32;
   void* out_bf16;
   void* out_relu;
@@ -106,9 +109,10 @@ typedef struct ada_gemm_desc {
   int32_t force_bn;     /* 0 = auto, else 32/64/128/256 */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
-/* out[rows or B*(n_tok-1), D] bf16 = LayerNorm(x fp32 [rows, D]) (block.py:84,87; dinov2.py:337-340 when drop_cls). */
-int ada_op_layernorm(const float* x, const float* w, const float* b, void* out_bf16, int32_t rows, int32_t D, float eps,
-                     int32_t n_tok, int32_t drop_cls, void* stream);
+/* out[rows or B*(n_tok-1), D] bf16 = LayerNorm(x + delta) (block.py:84,87,105-106; dinov2.py:337-340 when drop_cls).
+ * x fp32 [rows, D]; delta (optional, bf16 [rows, D]) is the pending residual-branch output; write_x stores x + delta back. */
+int ada_op_layernorm(float* x, const void* delta_bf16, const float* w, const float* b, void* out_bf16, int32_t rows,
+                     int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x, void* stream);
 /* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
 int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
 /* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */
