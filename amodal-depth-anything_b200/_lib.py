@@ -68,6 +68,7 @@ class GemmDesc(ctypes.Structure):
         ("cout", c_int32),
         ("sigmoid", c_int32),
         ("force_bn", c_int32),
+        ("force_cg", c_int32),
     ]
 
 

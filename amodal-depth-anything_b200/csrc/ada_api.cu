@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -87,19 +88,30 @@ static void require_device() {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM launcher
-template <int BN>
+template <int BN, int CG>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                            const GemmArgs& g, int num_tiles, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int grid = std::min(num_tiles, device_info().sms);
-  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, tc2, g);
-  ADA_CHECK_CUDA(cudaGetLastError());
+  const int units = std::min(num_tiles, device_info().sms / CG);  // persistent: one CTA (or CTA pair) per SM (pair)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  ADA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, ta, tb, tc, tc2, g));
 }
 
 static int pick_bn(int N) {
@@ -125,7 +137,13 @@ struct GemmLaunch {
   GemmArgs args{};           // epilogue fields filled by caller
   __nv_bfloat16* out_relu = nullptr;  // EPI_BF16: optional relu(out) copy (second TMA store map)
   int force_bn = 0;
+  int force_cg = 0;          // 0 = auto, 1 = single CTA tiles, 2 = CTA pairs (cta_group::2)
 };
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 static int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
 
@@ -171,13 +189,30 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_REQUIRE(bn != 32 || g.epi == EPI_TAIL, "BN=32 is only built for the fused tail epilogue");
   ADA_REQUIRE(g.epi != EPI_SWIGLU || L.N % 128 == 0, "SwiGLU needs N % 128 == 0");
   ADA_REQUIRE(L.ldb % 8 == 0, "weight pitch must be a multiple of 8 elements");
+  // ---- CTA pairs (cta_group::2) when the problem is big enough to keep 74 pairs busy and pairing wastes little
+  int cg = 1;
+  {
+    static const int cg_env = env_int("ADA_GEMM_CG", 0);
+    const int want = L.force_cg ? L.force_cg : cg_env;
+    const int tiles_n_ = (L.N + bn - 1) / bn;
+    bool ok = bn >= 128 && g.epi != EPI_TAIL;
+    if (ok && L.a_mode == A_CONV3X3) {
+      const int pad1 = (L.W + kTileW - 1) / kTileW * kTileW, pad2 = (L.W + 2 * kTileW - 1) / (2 * kTileW) * 2 * kTileW;
+      const long long pairs = static_cast<long long>(L.batch) * ((L.H + kTileH - 1) / kTileH) * (pad2 / (2 * kTileW)) * tiles_n_;
+      if (want != 2) ok = (pad2 * 100 <= pad1 * 107) && pairs >= 2 * (device_info().sms / 2);
+    } else if (ok) {
+      const long long pairs = static_cast<long long>((L.M + 2 * kBlockM - 1) / (2 * kBlockM)) * tiles_n_;
+      if (want != 2) ok = pairs >= 2 * (device_info().sms / 2);
+    }
+    if (ok && want != 1) cg = 2;
+  }
   CUtensorMap ta, tb;
   int tiles_m;
   if (L.a_mode == A_CONV3X3) {
     ADA_REQUIRE(L.Cin % 8 == 0, "conv Cin must be a multiple of 8");
     g.H = L.H;
     g.W = L.W;
-    g.tiles_x = (L.W + kTileW - 1) / kTileW;
+    g.tiles_x = (L.W + kTileW * cg - 1) / (kTileW * cg);
     g.tiles_y = (L.H + kTileH - 1) / kTileH;
     g.c_chunks = round_up(L.Cin, kBlockK) / kBlockK;
     g.K = 9 * g.c_chunks * kBlockK;
@@ -193,10 +228,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     ADA_REQUIRE(L.lda % 8 == 0, "A pitch must be a multiple of 8 elements");
     ta = make_tmap_2d(L.A, static_cast<uint64_t>(L.K), static_cast<uint64_t>(L.M), static_cast<uint64_t>(L.lda), kBlockK,
                       kBlockM);
-    tiles_m = (L.M + kBlockM - 1) / kBlockM;
+    tiles_m = (L.M + kBlockM * cg - 1) / (kBlockM * cg);
   }
   tb = make_tmap_2d(L.Bw, static_cast<uint64_t>(g.K), static_cast<uint64_t>(L.N), static_cast<uint64_t>(L.ldb), kBlockK,
-                    static_cast<uint32_t>(bn));
+                    static_cast<uint32_t>(bn / cg));
   // output maps for the TMA-store epilogues (dummy = tb otherwise; never dereferenced)
   CUtensorMap tc = tb, tc2 = tb;
   g.has_relu_copy = 0;
@@ -230,13 +265,18 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     prof.r->m = L.M;
     prof.r->n = L.N;
     prof.r->k = static_cast<int>(kreal);
-    prof.r->tag = g.epi | (g.act << 4) | (bn << 8);
+    prof.r->tag = g.epi | (g.act << 4) | (bn << 8) | (cg << 20);
   }
-  switch (bn) {
-    case 32: launch_gemm_bn<32>(ta, tb, tc, tc2, g, num_tiles, st); break;
-    case 64: launch_gemm_bn<64>(ta, tb, tc, tc2, g, num_tiles, st); break;
-    case 128: launch_gemm_bn<128>(ta, tb, tc, tc2, g, num_tiles, st); break;
-    default: launch_gemm_bn<256>(ta, tb, tc, tc2, g, num_tiles, st); break;
+  if (cg == 2) {
+    if (bn == 128) launch_gemm_bn<128, 2>(ta, tb, tc, tc2, g, num_tiles, st);
+    else launch_gemm_bn<256, 2>(ta, tb, tc, tc2, g, num_tiles, st);
+  } else {
+    switch (bn) {
+      case 32: launch_gemm_bn<32, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
+      case 64: launch_gemm_bn<64, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
+      case 128: launch_gemm_bn<128, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
+      default: launch_gemm_bn<256, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
+    }
   }
   ++g_launches;
 }
@@ -1225,6 +1265,7 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     L.W = d->W;
     L.Cin = d->Cin;
     L.force_bn = d->force_bn;
+    L.force_cg = d->force_cg;
     GemmArgs& e = L.args;
     e.epi = d->epi;
     e.act = d->act;

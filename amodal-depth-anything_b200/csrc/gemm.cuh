@@ -1,9 +1,15 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * B[N,K]^T).
 //
 //   warp 0      : TMA producer  (A and B tiles, 128-byte swizzle, 4..8 stage mbarrier ring)
-//   warp 1      : MMA issuer    (tcgen05.mma cta_group::1, 128 x BN x 16, fp32 accumulators in TMEM, 2 accumulator stages)
+//   warp 1      : MMA issuer    (tcgen05.mma, 128 x BN x 16 per CTA, fp32 accumulators in TMEM, 2 accumulator stages)
 //   warp 2      : TMEM allocator
 //   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem -> TMA store)
+//
+// CG = 2 runs the kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x BN tile, each CTA
+// loads its own 128 rows of A but only HALF of the B tile, and the leader CTA issues one 256 x BN x 16 MMA that reads
+// both halves. Operand traffic from L2 per FLOP drops by a third (the 128 x 256 single-CTA tile was L2->SM bound at
+// ~1.35 PFLOP/s) and shared-memory reads of B halve. Barriers: both producers credit the leader's `full` barrier,
+// tcgen05.commit multicasts `empty` / `tmem-full` to both CTAs, both epilogues release the leader's `tmem-empty`.
 //
 // The A operand is fetched either as a plain row-major matrix (linear layers, 1x1 convs, transposed convs with k == s)
 // or as an implicit-GEMM 3x3/pad-1/stride-1 convolution over an NHWC map: the M tile is an 8x16 pixel patch and each
@@ -62,12 +68,14 @@ struct GemmArgs {
   int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBRows = BN / CG;                         // B rows (N) loaded by one CTA
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStagesFit = (232448 - 4 * 2 * 4096 - 2 * 256 * 4 - 256) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
   static constexpr int kStagingBytes = 4 * 2 * 4096;             // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
@@ -78,18 +86,18 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
-// Exact-erf GELU (nn.GELU default, mlp.py:30-41). erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
-// bf16 rounding of the stored activation): 2 MUFU ops + ~12 FMAs instead of erff's branchy ~40 instructions.
+// GELU with the exact-erf definition (nn.GELU default, mlp.py:30-41): gelu(x) = x * Phi(x). Phi is evaluated as
+// sigmoid(x * q(x^2)) with q a degree-2 minimax fit (scipy, x in [-8, 8]) of logit(Phi(x)) / x:
+//   max |approx - x * 0.5 * (1 + erf(x / sqrt 2))| = 2.5e-5, below half a bf16 ulp of any stored value above 6e-3.
+// 6 FMA-pipe ops + 1 ALU op + 2 MUFU per element; the epilogue is FP32-issue bound (3-register FMA-pipe ops issue every
+// other cycle), and the previous Abramowitz-Stegun form (~22 ops) kept fc1 at 666 TFLOP/s vs 1221 for the plain epilogue.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = fast_exp2(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  constexpr float kL2e = 1.4426950408889634f;
+  const float s = fminf(x * x, 50.0f);  // q is monotone on [0, 52]; beyond |x| = 7 the sigmoid is saturated anyway
+  float q = fmaf(-0.0007030335770476013f * -kL2e, s, 0.07401129204396431f * -kL2e);
+  q = fmaf(q, s, 1.5950157685717141f * -kL2e);
+  const float e = fast_exp2(x * q);    // exp(-x q(x^2))
+  return x * fast_rcp(1.0f + e);
 }
 
 __device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4 rr) {
@@ -97,12 +105,13 @@ __device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4 rr) {
   v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
+  static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   uint8_t* smem_gen = smem_raw;
@@ -123,42 +132,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 issues the MMAs
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), CG);   // one arrive.expect_tx per producing CTA (leader's barrier is the one used)
+      mbar_init(empty_bar(s), 1);   // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+  // A tile = CG stacked 128-row sub-tiles (linear) or CG horizontally adjacent 8x16 pixel patches (conv; g.tiles_x
+  // already counts 16*CG-pixel wide tiles). Work unit = CTA pair when CG == 2.
   const int tiles_n = (g.N + BN - 1) / BN;
   const int tiles_m = (g.a_mode == A_CONV3X3) ? (g.M / (g.H * g.W)) * g.tiles_x * g.tiles_y
-                                              : (g.M + kBlockM - 1) / kBlockM;
+                                              : (g.M + kBlockM * CG - 1) / (kBlockM * CG);
   const int num_tiles = tiles_m * tiles_n;
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
   const int num_kb = (g.a_mode == A_CONV3X3) ? 9 * g.c_chunks : (g.K + kBlockK - 1) / kBlockK;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = unit; t < num_tiles; t += num_units) {
       const int mt = t / tiles_n, nt = t % tiles_n;
       int img = 0, y0 = 0, x0 = 0;
       if (g.a_mode == A_CONV3X3) {
@@ -166,35 +184,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         img = mt / per_img;
         const int r = mt % per_img;
         y0 = (r / g.tiles_x) * kTileH;
-        x0 = (r % g.tiles_x) * kTileW;
+        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) * kTileW;
       }
+      const int m_row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM;
+      const int n_row0 = nt * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
         if (lane == 0) {
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if (g.a_mode == A_CONV3X3) {
-            const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
-            const int ky = tap / 3, kx = tap % 3;
-            tma_load_4d(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+          if constexpr (CG == 2) {
+            const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+            mbar_expect_tx_cluster(fb, Cfg::kStageBytes);
+            if (g.a_mode == A_CONV3X3) {
+              const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
+              const int ky = tap / 3, kx = tap % 3;
+              tma_load_4d_cg2(sa, &tmap_a, fb, cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+            } else {
+              tma_load_2d_cg2(sa, &tmap_a, fb, kb * kBlockK, m_row0);
+            }
+            tma_load_2d_cg2(sb, &tmap_b, fb, kb * kBlockK, n_row0);
           } else {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, mt * kBlockM);
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            if (g.a_mode == A_CONV3X3) {
+              const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
+              const int ky = tap / 3, kx = tap % 3;
+              tma_load_4d(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+            } else {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_row0);
+            }
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_row0);
           }
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, nt * BN);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of the pair)
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = unit; t < num_tiles; t += num_units) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200 + acc);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -208,10 +241,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaK * 2, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaK * 2, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2)
+              umma_bf16_ss_cg2(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+          if constexpr (CG == 2) {
+            umma_commit_cg2(empty_bar(stage), 0x3);                 // frees this smem slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_cg2(tfull_bar(acc), 0x3);  // accumulator complete, both epilogues
+          } else {
+            umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -230,7 +271,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool tma_out = (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = unit; t < num_tiles; t += num_units) {
       const int mt = t / tiles_n, nt = t % tiles_n;
       const int n0 = nt * BN;
       // ---- map accumulator row -> output row
@@ -243,14 +284,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         img = mt / per_img;
         const int r = mt % per_img;
         y0 = (r / g.tiles_x) * kTileH;
-        x0 = (r % g.tiles_x) * kTileW;
+        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) * kTileW;
         const int y = y0 + row / kTileW;
         const int x = x0 + row % kTileW;
         valid = (y < g.H) && (x < g.W);
         orow = (static_cast<long long>(img) * g.H + y) * g.W + x;
         m = static_cast<int>(orow);
       } else {
-        m = mt * kBlockM + row;
+        m = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + row;
         valid = m < g.M;
         orow = m;
       }
@@ -299,8 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int j = 0; j < 32; j += 2) {
                   const float x1a = __uint_as_float(a[j]) + bb[j], x1b = __uint_as_float(a[j + 1]) + bb[j + 1];
                   const float x2a = __uint_as_float(b[j]) + bb[32 + j], x2b = __uint_as_float(b[j + 1]) + bb[33 + j];
-                  const float ha = __fdividef(x1a, 1.0f + __expf(-x1a)) * x2a;
-                  const float hb = __fdividef(x1b, 1.0f + __expf(-x1b)) * x2b;
+                  const float ha = x1a * fast_rcp(1.0f + fast_exp2(x1a * -1.4426950408889634f)) * x2a;
+                  const float hb = x1b * fast_rcp(1.0f + fast_exp2(x1b * -1.4426950408889634f)) * x2b;
                   pk[h * 16 + (j >> 1)] = pack_bf16x2(ha, hb);
                 }
               }
@@ -316,7 +357,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int gi = 0; gi < 4; ++gi) {
                   float v[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[gi * 8 + j]) + bb[gi * 8 + j]) * gg[gi * 8 + j];
+                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gi * 8 + j]) + bb[gi * 8 + j];
+                  if (g.gamma != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] *= gg[gi * 8 + j];
+                  }
                   if (g.act == ACT_GELU) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
@@ -363,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (g.a_mode == A_CONV3X3)
                   tma_store_4d(tm, buf, oc, x0, y0 + 2 * q, img);
                 else
-                  tma_store_2d(tm, buf, oc, mt * kBlockM + q * 32);
+                  tma_store_2d(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
                 bulk_commit();
               }
               sbuf ^= 1;
@@ -440,7 +485,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // accumulator stage drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG == 2)
+          mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));  // the leader's MMA warp owns the accumulator hand-off
+        else
+          mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) bulk_wait<0>();  // all TMA stores of this warp have completed before the CTA retires
@@ -448,10 +498,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still read our smem / TMEM until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

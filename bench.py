@@ -249,7 +249,7 @@ def main():
             agg = {}
             for i in range(max(nrec, 0)):
                 c, m_, n_, k_, tag = meta[5 * i:5 * i + 5]
-                key = f"{PROF_CLASSES[c]} M={m_} N={n_} K={k_} epi={tag & 15} act={(tag >> 4) & 15} bn={tag >> 8}"
+                key = f"{PROF_CLASSES[c]} M={m_} N={n_} K={k_} epi={tag & 15} act={(tag >> 4) & 15} bn={(tag >> 8) & 0xfff} cg={tag >> 20}"
                 e = agg.setdefault(key, {"ms": 0.0, "n": 0, "flops": 2.0 * m_ * n_ * k_})
                 e["ms"] += rms[i]
                 e["n"] += 1

@@ -107,6 +107,7 @@ typedef struct ada_gemm_desc {
   const float* aux;
   int32_t ldo, P, ks, cout, sigmoid;
   int32_t force_bn;     /* 0 = auto, else 32/64/128/256 */
+  int32_t force_cg;     /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
 /* out[rows or B*(n_tok-1), D] bf16 = LayerNorm(x + delta) (block.py:84,87,105-106; dinov2.py:337-340 when drop_cls).

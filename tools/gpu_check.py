@@ -32,7 +32,7 @@ def _cmp(name, got, ref, atol, rtol):
     return res
 
 
-def chk_gemm(M, N, K, bn, epi_name):
+def chk_gemm(M, N, K, bn, epi_name, cg=0):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(1)
     A = (torch.randn(M, K, generator=g, device="cuda") * 0.5).bfloat16()
@@ -41,16 +41,16 @@ def chk_gemm(M, N, K, bn, epi_name):
     ref = A.float() @ Wt.float().t() + bias
     if epi_name == "bias":
         out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
-        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, force_bn=bn)
+        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, force_bn=bn, force_cg=cg)
     elif epi_name == "gelu":
         out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
-        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, act=L.ACT_GELU, force_bn=bn)
+        ops.gemm(A, Wt, bias=bias, out_bf16=out, ldo=N, act=L.ACT_GELU, force_bn=bn, force_cg=cg)
         ref = torch.nn.functional.gelu(ref)
     elif epi_name == "resid":  # LayerScale'd branch output (bf16); the residual add itself is fused into the next LN
         gamma = torch.randn(N, generator=g, device="cuda")
         ref = gamma * ref
         out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
-        ops.gemm(A, Wt, bias=bias, gamma=gamma, out_bf16=out, ldo=N, force_bn=bn)
+        ops.gemm(A, Wt, bias=bias, gamma=gamma, out_bf16=out, ldo=N, force_bn=bn, force_cg=cg)
     elif epi_name == "swiglu":
         Hd = N // 2
         # interleave rows in 32-chunks exactly like ada_finalize does
@@ -58,7 +58,7 @@ def chk_gemm(M, N, K, bn, epi_name):
         chunk, within = idx // 64, idx % 64
         src = torch.where(within < 32, chunk * 32 + within, Hd + chunk * 32 + within - 32)
         out = torch.zeros(M, Hd, dtype=torch.bfloat16, device="cuda")
-        ops.gemm(A, Wt[src].contiguous(), epi=L.EPI_SWIGLU, bias=bias[src].contiguous(), out_bf16=out, ldo=Hd, force_bn=bn)
+        ops.gemm(A, Wt[src].contiguous(), epi=L.EPI_SWIGLU, bias=bias[src].contiguous(), out_bf16=out, ldo=Hd, force_bn=bn, force_cg=cg)
         x1, x2 = ref[:, :Hd], ref[:, Hd:]
         ref = torch.nn.functional.silu(x1) * x2
     torch.cuda.synchronize()
@@ -83,7 +83,7 @@ def chk_embed():
     return r
 
 
-def chk_conv(B, H, W, Cin, Cout, mode):
+def chk_conv(B, H, W, Cin, Cout, mode, cg=0):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(3)
     x = (torch.randn(B, Cin, H, W, generator=g, device="cuda")).bfloat16()
@@ -95,7 +95,7 @@ def chk_conv(B, H, W, Cin, Cout, mode):
     ref = torch.nn.functional.conv2d(x.float(), wq, bias, padding=1)
     if mode == "plain":
         out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
-        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, bias=bias, out_bf16=out, ldo=Cout)
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, bias=bias, out_bf16=out, ldo=Cout, force_cg=cg)
         torch.cuda.synchronize()
         return _cmp("conv", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
     if mode == "rcu":  # relu act + two residuals + relu copy
@@ -104,7 +104,7 @@ def chk_conv(B, H, W, Cin, Cout, mode):
         out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
         outr = torch.zeros_like(out)
         ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, bias=bias, act=L.ACT_RELU, resid1=r1, resid2=r2, out_bf16=out,
-                 out_relu=outr, ldo=Cout)
+                 out_relu=outr, ldo=Cout, force_cg=cg)
         torch.cuda.synchronize()
         ref2 = torch.relu(ref).permute(0, 2, 3, 1) + r1.float() + r2.float()
         a = _cmp("conv", out, ref2, 3e-2, 1e-2)
@@ -257,6 +257,14 @@ CHECKS = {
     "gemm_ragged_n": lambda: chk_gemm(500, 48, 384, 0, "bias"),
     "gemm_swiglu": lambda: chk_gemm(700, 1024, 256, 0, "swiglu"),
     "gemm_embed": chk_embed,
+    "gemm_cg2_small": lambda: chk_gemm(300, 256, 128, 256, "bias", cg=2),
+    "gemm_cg2_bn128": lambda: chk_gemm(700, 384, 192, 128, "bias", cg=2),
+    "gemm_cg2_qkv": lambda: chk_gemm(1370 * 2, 3072, 1024, 0, "bias", cg=2),
+    "gemm_cg2_gelu": lambda: chk_gemm(1370, 4096, 1024, 0, "gelu", cg=2),
+    "gemm_cg2_gamma": lambda: chk_gemm(1370, 1024, 4096, 0, "resid", cg=2),
+    "gemm_cg2_swiglu": lambda: chk_gemm(700, 1024, 256, 0, "swiglu", cg=2),
+    "conv_cg2_plain": lambda: chk_conv(2, 37, 45, 128, 256, "plain", cg=2),
+    "conv_cg2_rcu": lambda: chk_conv(2, 19, 33, 64, 128, "rcu", cg=2),
     "conv_plain_37": lambda: chk_conv(2, 37, 37, 128, 64, "plain"),
     "conv_c48": lambda: chk_conv(1, 20, 33, 48, 48, "plain"),
     "conv_rcu": lambda: chk_conv(2, 19, 19, 64, 64, "rcu"),
