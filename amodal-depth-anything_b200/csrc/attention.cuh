@@ -6,11 +6,16 @@
 // through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
 //   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
 //   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)  -> TMEM cols [0,128)
-//                                 O_j = P V  (128x64x128, P K-major from smem, V MN-major) -> TMEM cols [128,192)
-//   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane), so row max / row sum need no shuffles.
-//                P is written to shared memory as bf16 in the 128-byte-swizzled K-major layout the MMA expects;
-//                the running output lives in registers: O = O * alpha + O_j.
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+//                                 O += P V   (128x64x128, P K-major from smem, V MN-major) -> TMEM cols [128,192)
+//   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane): the whole 128-wide score row is pulled into
+//                registers with four back-to-back tcgen05.ld (one wait), so row max / row sum need no shuffles and S is
+//                released to the MMA warp before the exponentials start (S(j+1) overlaps softmax(j)).
+//                P goes to shared memory as bf16 in the 128-byte-swizzled K-major layout the MMA expects.
+// The running output stays in TMEM across KV tiles (P V accumulates in place). Rows are kept relative to a *stale* maximum:
+// the accumulator is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row's maximum grows by more than 2^8,
+// which happens in the first tile or two; p may then reach 256, harmless in fp32/bf16, and O / l is exact either way.
+// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
+// The kernel is MUFU (ex2) bound at head_dim 64: 128x128 exponentials per tile = 1024 cycles/SM vs 512 cycles of MMA.
 #pragma once
 #include "ptx.cuh"
 
@@ -20,6 +25,7 @@ constexpr int kAttThreads = 192;
 constexpr int kAttQ = 128, kAttKV = 128, kAttD = 64;
 constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 256 /*barriers*/;
 constexpr int kAttTmemCols = 256;
+constexpr float kAttRescaleLog2 = 8.0f;  // rescale O only when a row max grows by more than 2^8
 
 struct AttArgs {
   int B, N, heads, D;        // D = heads * 64
@@ -33,12 +39,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
   const uint32_t sbase = smem_u32(att_smem);
   const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152, sP = sbase + 81920;
   const uint32_t bar = sbase + 114688;
-  const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24;
-  auto k_full = [&](int s) { return bar + 32 + 8u * s; };
-  auto k_empty = [&](int s) { return bar + 48 + 8u * s; };
-  auto v_full = [&](int s) { return bar + 64 + 8u * s; };
-  auto v_empty = [&](int s) { return bar + 80 + 8u * s; };
-  const uint32_t tmem_ptr_smem = bar + 96;
+  const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24, s_free = bar + 32;
+  auto k_full = [&](int s) { return bar + 40 + 8u * s; };
+  auto k_empty = [&](int s) { return bar + 56 + 8u * s; };
+  auto v_full = [&](int s) { return bar + 72 + 8u * s; };
+  auto v_empty = [&](int s) { return bar + 88 + 8u * s; };
+  const uint32_t tmem_ptr_smem = bar + 104;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAttQ, head = blockIdx.y, img = blockIdx.z;
@@ -54,6 +60,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
+    mbar_init(s_free, 128);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
@@ -118,8 +125,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     issue_s(0);
     for (int j = 0; j < num_kv; ++j) {
       const int s = j & 1;
-      mbar_wait(p_full, j & 1, 0x540);  // S(j) consumed, O_{j-1} consumed, P(j) in smem
-      if (j + 1 < num_kv) issue_s(j + 1);
+      if (j + 1 < num_kv) {
+        mbar_wait(s_free, j & 1, 0x535);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
+        issue_s(j + 1);
+      }
+      mbar_wait(p_full, j & 1, 0x540);    // P(j) in smem, O rescaled if needed
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
@@ -127,7 +137,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sV + s * 16384 + kk * 2048, 0, 1024);
-          umma_bf16_ss(tO, da, db, idesc_o, kk > 0 ? 1u : 0u);
+          umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(v_empty(s));
         umma_commit(o_full);
@@ -140,10 +150,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float c = a.scale_log2e;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
     const uint32_t p_row = sP + row * 128;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
 
@@ -151,91 +158,107 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       const int kv_valid = min(kAttKV, a.N - j * kAttKV);
       mbar_wait(s_full, j & 1, 0x560);
       tc_fence_after();
-      // pass 1: row max over this KV tile
-      float mx = m_run;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + cc * 32, r);
-        tmem_ld_wait();
-        if (kv_valid == kAttKV) {
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(tS + lane_off, s0);
+      tmem_ld32(tS + lane_off + 32, s1);
+      tmem_ld32(tS + lane_off + 64, s2);
+      tmem_ld32(tS + lane_off + 96, s3);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(j) now lives in registers
+      if (kv_valid < kAttKV) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) s0[i] = 0xff800000u;
+          if (32 + i >= kv_valid) s1[i] = 0xff800000u;
+          if (64 + i >= kv_valid) s2[i] = 0xff800000u;
+          if (96 + i >= kv_valid) s3[i] = 0xff800000u;
         }
       }
-      const float alpha = fast_exp2((m_run - mx) * c);  // first tile: exp2(-inf) = 0
-      m_run = mx;
-      const float mc = mx * c;
-      // fold the previous tile's P V into the running output
+      float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        t0 = fmaxf(t0, __uint_as_float(s0[i]));
+        t1 = fmaxf(t1, __uint_as_float(s1[i]));
+        t2 = fmaxf(t2, __uint_as_float(s2[i]));
+        t3 = fmaxf(t3, __uint_as_float(s3[i]));
+      }
+      const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+
+      // P(j-1) V(j-1) must have retired before P's buffer is overwritten (and before O may be rescaled)
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1, 0x570);
         tc_fence_after();
+      }
+      if (j == 0) {
+        m_used = tmax;
+      } else {
+        const bool grow = (tmax - m_used) * c > kAttRescaleLog2;
+        if (__any_sync(0xffffffffu, grow)) {  // rare: bring this warp's 32 accumulator rows to the new maxima
+          const float m_new = fmaxf(m_used, tmax);
+          const float sc = fast_exp2((m_used - m_new) * c);
+          m_used = m_new;
+          l_run *= sc;
+#pragma unroll 1
+          for (int h = 0; h < 8; ++h) {  // 8 columns at a time: this path is rare, keep its register footprint small
+            uint32_t r[8];
+            tmem_ld8(tO + lane_off + h * 8, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r[32];
-          tmem_ld32(tO + lane_off + h * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_pending, __uint_as_float(r[i]));
+            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
+            tmem_st8(tO + lane_off + h * 8, r);
+          }
+          tmem_st_wait();
         }
       }
-      alpha_pending = alpha;
-      // pass 2: P = exp2(S*c - m*c) -> bf16 -> swizzled smem; row sum in fp32
-      float rs = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + cc * 32, r);
-        tmem_ld_wait();
+      const float mc = m_used * c;
+      float rs0 = 0.f, rs1 = 0.f;
+      auto emit = [&](const uint32_t (&sv)[32], int cc) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), c, -mc));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
-          if (cc * 32 + i >= kv_valid) p0 = 0.f;
-          if (cc * 32 + i + 1 >= kv_valid) p1 = 0.f;
-          rs += p0 + p1;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
+          rs0 += p0;
+          rs1 += p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         const uint32_t sub = p_row + (cc >> 1) * 16384;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + i);
-          const uint32_t addr = sub + ((chunk ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
-                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
-                       : "memory");
+          st_shared_v4(sub + ((chunk ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
-      }
-      l_run = fmaf(l_run, alpha, rs);
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
+      l_run += rs0 + rs1;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // last P V
+    // ---- epilogue: O / l -> bf16
     mbar_wait(o_full, (num_kv - 1) & 1, 0x580);
     tc_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* orow = a.out + (static_cast<long long>(img) * a.N + min(qi, a.N - 1)) * a.D + head * kAttD;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t r[32];
       tmem_ld32(tO + lane_off + h * 32, r);
       tmem_ld_wait();
+      if (qi < a.N) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + h * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_pending, __uint_as_float(r[i]));
-    }
-    const int qi = q0 + row;
-    if (qi < a.N) {
-      const float inv = 1.0f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(img) * a.N + qi) * a.D + head * kAttD);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                            pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
-                            pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+        for (int i = 0; i < 4; ++i) {
+          dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
+                              pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
+                              pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
+                              pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
+        }
       }
     }
   }

@@ -140,11 +140,15 @@ def chk_convT(ks):
     return _cmp("convT", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
 
 
-def chk_attention(B, N, heads):
+def chk_attention(B, N, heads, grow=False):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(5)
     D = heads * 64
-    qkv = (torch.randn(B, N, 3, heads, 64, generator=g, device="cuda") * 1.5).bfloat16()
+    qkv = torch.randn(B, N, 3, heads, 64, generator=g, device="cuda") * 1.5
+    if grow:  # key norms grow along the sequence -> row maxima jump by > 2^8 between KV tiles (exercises the O rescale)
+        ramp = 1.0 + 7.0 * (torch.arange(N, device="cuda") // 128).float() / max((N - 1) // 128, 1)
+        qkv[:, :, 1] *= ramp.view(1, N, 1, 1)
+    qkv = qkv.bfloat16()
     out = ops.attention(qkv, B, N, heads)
     torch.cuda.synchronize()
     q, k, v = [t.float().permute(0, 2, 1, 3) for t in qkv.unbind(2)]  # [B,h,N,64]
@@ -274,6 +278,8 @@ CHECKS = {
     "attention_small": lambda: chk_attention(1, 128, 1),
     "attention_ragged": lambda: chk_attention(1, 200, 2),
     "attention_1370": lambda: chk_attention(2, 1370, 6),
+    "attention_rescale": lambda: chk_attention(1, 1370, 2, grow=True),
+    "attention_5477": lambda: chk_attention(1, 5477, 2),
     "layernorm_384": lambda: chk_layernorm(384, False),
     "layernorm_1024_drop": lambda: chk_layernorm(1024, True),
     "layernorm_1536": lambda: chk_layernorm(1536, False),
