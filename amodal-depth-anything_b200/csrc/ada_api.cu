@@ -342,7 +342,14 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
   ADA_REQUIRE(C % 8 == 0, "upsample: C % 8");
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
   ProfScope prof(PC_UPSAMPLE, 0.0, 2.0 * B * C * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
-  upsample_bilinear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, Hi, Wi, Ho, Wo, C);
+  const int groups = C / 8;
+  int shift = -1;
+  for (int sft = 0; sft < 12; ++sft)
+    if ((1 << sft) == groups) shift = sft;
+  dim3 grid(static_cast<unsigned>((static_cast<long long>(Wo) * groups + 255) / 256), static_cast<unsigned>(Ho),
+            static_cast<unsigned>(B));
+  (void)total;
+  upsample_bilinear_kernel<<<grid, 256, 0, st>>>(in, out, Hi, Wi, Ho, Wo, C, shift);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }

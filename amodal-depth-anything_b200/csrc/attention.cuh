@@ -6,15 +6,17 @@
 // through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
 //   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
 //   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)  -> TMEM cols [0,128)
-//                                 O += P V   (128x64x128, P K-major from smem, V MN-major) -> TMEM cols [128,192)
+//                                 O += P V   (128x64x128, P from TMEM, V MN-major from smem) -> TMEM cols [192,256)
 //   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane): the whole 128-wide score row is pulled into
 //                registers with four back-to-back tcgen05.ld (one wait), so row max / row sum need no shuffles and S is
 //                released to the MMA warp before the exponentials start (S(j+1) overlaps softmax(j)).
-//                P goes to shared memory as bf16 in the 128-byte-swizzled K-major layout the MMA expects.
+//                P is written back to TMEM (cols [128,192), bf16 pairs) with tcgen05.st and consumed as the A operand
+//                of the P V MMA straight from there: shared memory only carries Q/K/V (its bandwidth, 128 B/clk, was
+//                the co-bottleneck when P went through a 32 KB swizzled smem tile).
 // The running output stays in TMEM across KV tiles (P V accumulates in place). Rows are kept relative to a *stale* maximum:
 // the accumulator is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row's maximum grows by more than 2^8,
 // which happens in the first tile or two; p may then reach 256, harmless in fp32/bf16, and O / l is exact either way.
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
+// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
 // The kernel is MUFU (ex2) bound at head_dim 64: 128x128 exponentials per tile = 1024 cycles/SM vs 512 cycles of MMA.
 #pragma once
 #include "ptx.cuh"
@@ -23,7 +25,7 @@ namespace ada {
 
 constexpr int kAttThreads = 192;
 constexpr int kAttQ = 128, kAttKV = 128, kAttD = 64;
-constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 256 /*barriers*/;
+constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 256 /*barriers*/;
 constexpr int kAttTmemCols = 256;
 constexpr float kAttRescaleLog2 = 8.0f;  // rescale O only when a row max grows by more than 2^8
 
@@ -37,8 +39,8 @@ __global__ void __launch_bounds__(kAttThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
-  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152, sP = sbase + 81920;
-  const uint32_t bar = sbase + 114688;
+  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152;
+  const uint32_t bar = sbase + 81920;
   const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24, s_free = bar + 32;
   auto k_full = [&](int s) { return bar + 40 + 8u * s; };
   auto k_empty = [&](int s) { return bar + 56 + 8u * s; };
@@ -78,7 +80,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -129,15 +131,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         mbar_wait(s_free, j & 1, 0x535);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
         issue_s(j + 1);
       }
-      mbar_wait(p_full, j & 1, 0x540);    // P(j) in smem, O rescaled if needed
+      mbar_wait(p_full, j & 1, 0x540);    // P(j) in TMEM, O rescaled if needed
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
           const uint64_t db = make_smem_desc_sw128(sV + s * 16384 + kk * 2048, 0, 1024);
-          umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tO, tP + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(v_empty(s));
         umma_commit(o_full);
@@ -151,8 +152,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float c = a.scale_log2e;
     float m_used = -INFINITY, l_run = 0.f;
-    const uint32_t p_row = sP + row * 128;
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
 
     for (int j = 0; j < num_kv; ++j) {
       const int kv_valid = min(kAttKV, a.N - j * kAttKV);
@@ -185,7 +184,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       }
       const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
 
-      // P(j-1) V(j-1) must have retired before P's buffer is overwritten (and before O may be rescaled)
+      // P(j-1) V(j-1) must have retired before P's TMEM columns are overwritten (and before O may be rescaled)
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1, 0x570);
         tc_fence_after();
@@ -213,29 +212,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       }
       const float mc = m_used * c;
       float rs0 = 0.f, rs1 = 0.f;
-      auto emit = [&](const uint32_t (&sv)[32], int cc) {
-        uint32_t pk[16];
+      auto emit = [&](const uint32_t (&sa)[32], const uint32_t (&sb)[32], int half) {  // 64 keys -> 32 packed columns
+        uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sa[i]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sa[i + 1]), c, -mc));
           rs0 += p0;
           rs1 += p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        const uint32_t sub = p_row + (cc >> 1) * 16384;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + i);
-          st_shared_v4(sub + ((chunk ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sb[i]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sb[i + 1]), c, -mc));
+          rs0 += p0;
+          rs1 += p1;
+          pk[16 + (i >> 1)] = pack_bf16x2(p0, p1);
         }
+        tmem_st32(tP + lane_off + half * 32, pk);
       };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
+      emit(s0, s1, 0);
+      emit(s2, s3, 1);
+      tmem_st_wait();
       l_run += rs0 + rs1;
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }

@@ -202,17 +202,15 @@ im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict
 // Bilinear upsampling, align_corners=True (blocks.py:144, dpt.py:194), NHWC bf16. One thread per 8 channels.
 // Index math mirrors ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1).
 __global__ void __launch_bounds__(256)
-upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Hi, int Wi,
-                         int Ho, int Wo, int C) {
+upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Hi, int Wi, int Ho,
+                         int Wo, int C, int groups_shift) {
+  // grid: x over (xo, 8-channel group), y = output row, z = image: no 64-bit div/mod on the hot path
   const int groups = C >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * groups;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gi = static_cast<int>(idx % groups);
-  long long t = idx / groups;
-  const int xo = static_cast<int>(t % Wo); t /= Wo;
-  const int yo = static_cast<int>(t % Ho);
-  const int b = static_cast<int>(t / Ho);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xo = (groups_shift >= 0) ? (i >> groups_shift) : (i / groups);
+  const int gi = i - xo * groups;
+  if (xo >= Wo) return;
+  const int yo = blockIdx.y, b = blockIdx.z;
   const float sh = (Ho > 1) ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
   const float fy = sh * yo, fx = sw * xo;
@@ -221,10 +219,10 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
   const float ly = fy - y0, lx = fx - x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
   const __nv_bfloat16* base = in + static_cast<long long>(b) * Hi * Wi * C + gi * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * C);
-  const uint4 bq = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * C);
-  const uint4 c = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * C);
-  const uint4 d = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * C);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * C));
+  const uint4 bq = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * C));
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * C));
+  const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * C));
   const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {c.x, c.y, c.z, c.w},
                  dv[4] = {d.x, d.y, d.z, d.w};
   uint32_t o[4];
@@ -234,7 +232,8 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
     const float hi = hy * (hx * bf16_hi(av[j]) + lx * bf16_hi(bv[j])) + ly * (hx * bf16_hi(cv[j]) + lx * bf16_hi(dv[j]));
     o[j] = pack_bf16x2(lo, hi);
   }
-  *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  __nv_bfloat16* dst = out + ((static_cast<long long>(b) * Ho + yo) * Wo + xo) * C + gi * 8;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 }  // namespace ada
