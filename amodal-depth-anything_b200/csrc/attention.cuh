@@ -184,20 +184,48 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       }
       const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
 
-      // P(j-1) V(j-1) must have retired before P's TMEM columns are overwritten (and before O may be rescaled)
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1, 0x570);
-        tc_fence_after();
-      }
+      // ---- running (stale) maximum: decide now, in registers; the accumulator itself is rescaled further down
+      float sc = 1.0f;
+      bool rescale = false;
       if (j == 0) {
         m_used = tmax;
       } else {
         const bool grow = (tmax - m_used) * c > kAttRescaleLog2;
-        if (__any_sync(0xffffffffu, grow)) {  // rare: bring this warp's 32 accumulator rows to the new maxima
+        rescale = __any_sync(0xffffffffu, grow);  // rare (first tile or two)
+        if (rescale) {
           const float m_new = fmaxf(m_used, tmax);
-          const float sc = fast_exp2((m_used - m_new) * c);
+          sc = fast_exp2((m_used - m_new) * c);
           m_used = m_new;
           l_run *= sc;
+        }
+      }
+      const float mc = m_used * c;
+      float rs0 = 0.f, rs1 = 0.f;
+      // 64 keys -> 32 packed bf16x2 columns. 3 of every 8 exponentials run on the FMA pipe (exp2_fma), the rest on MUFU:
+      // ncu showed the XU pipe at 61% with FMA at 17%, i.e. the kernel is MUFU-bound at head_dim 64.
+      auto expo = [&](const uint32_t (&sa)[32], const uint32_t (&sb)[32], uint32_t (&pk)[32]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = fmaf(__uint_as_float(h ? sb[i] : sa[i]), c, -mc);
+            const float x1 = fmaf(__uint_as_float(h ? sb[i + 1] : sa[i + 1]), c, -mc);
+            const int e = (i >> 1) & 7;  // position within a group of 8 pairs
+            const float p0 = (e == 1 || e == 4 || e == 6) ? exp2_fma(x0) : fast_exp2(x0);
+            const float p1 = (e == 2 || e == 4 || e == 7) ? exp2_fma(x1) : fast_exp2(x1);
+            rs0 += p0;
+            rs1 += p1;
+            pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
+        }
+      };
+      uint32_t pk[32];
+      expo(s0, s1, pk);  // first half of the row before touching TMEM: hides the wait for P(j-1) V(j-1) below
+      // P(j-1) V(j-1) must have retired before P's TMEM columns are overwritten (and before O may be rescaled)
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1, 0x570);
+        tc_fence_after();
+        if (rescale) {  // bring this warp's 32 accumulator rows to the new maxima
 #pragma unroll 1
           for (int h = 0; h < 8; ++h) {  // 8 columns at a time: this path is rare, keep its register footprint small
             uint32_t r[8];
@@ -207,33 +235,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
             tmem_st8(tO + lane_off + h * 8, r);
           }
-          tmem_st_wait();
         }
       }
-      const float mc = m_used * c;
-      float rs0 = 0.f, rs1 = 0.f;
-      auto emit = [&](const uint32_t (&sa)[32], const uint32_t (&sb)[32], int half) {  // 64 keys -> 32 packed columns
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sa[i]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sa[i + 1]), c, -mc));
-          rs0 += p0;
-          rs1 += p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sb[i]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sb[i + 1]), c, -mc));
-          rs0 += p0;
-          rs1 += p1;
-          pk[16 + (i >> 1)] = pack_bf16x2(p0, p1);
-        }
-        tmem_st32(tP + lane_off + half * 32, pk);
-      };
-      emit(s0, s1, 0);
-      emit(s2, s3, 1);
+      tmem_st32(tP + lane_off, pk);
+      expo(s2, s3, pk);
+      tmem_st32(tP + lane_off + 32, pk);
       tmem_st_wait();
       l_run += rs0 + rs1;
       tc_fence_before();

@@ -284,6 +284,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, degree-3 minimax for 2^f (max relative
+// error 7.5e-5, far below the bf16 rounding of the attention probabilities it feeds), exponent patched with integer add.
+// Valid for x in [-125, 120]. Used for a fraction of the softmax exponentials, which are MUFU-bound at head_dim 64.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517166769240653f, 0.24261112208902955f);
+  p = fmaf(p, f, 0.6932609857127241f);
+  p = fmaf(p, f, 0.9999280735522232f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
