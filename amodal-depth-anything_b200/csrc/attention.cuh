@@ -174,15 +174,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
           if (96 + i >= kv_valid) s3[i] = 0xff800000u;
         }
       }
-      float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+      // 16 independent max chains (a single chain of 128 dependent FMNMX would cost 128 x 4 cycles of pure latency)
+      float tm[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        t0 = fmaxf(t0, __uint_as_float(s0[i]));
-        t1 = fmaxf(t1, __uint_as_float(s1[i]));
-        t2 = fmaxf(t2, __uint_as_float(s2[i]));
-        t3 = fmaxf(t3, __uint_as_float(s3[i]));
+      for (int i = 0; i < 4; ++i) {
+        tm[i] = fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 4]));
+        tm[4 + i] = fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 4]));
+        tm[8 + i] = fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 4]));
+        tm[12 + i] = fmaxf(__uint_as_float(s3[i]), __uint_as_float(s3[i + 4]));
       }
-      const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+#pragma unroll
+      for (int i = 8; i < 32; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tm[k] = fmaxf(tm[k], __uint_as_float(s0[i + k]));
+          tm[4 + k] = fmaxf(tm[4 + k], __uint_as_float(s1[i + k]));
+          tm[8 + k] = fmaxf(tm[8 + k], __uint_as_float(s2[i + k]));
+          tm[12 + k] = fmaxf(tm[12 + k], __uint_as_float(s3[i + k]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tm[i] = fmaxf(tm[i], tm[i + 8]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tm[i] = fmaxf(tm[i], tm[i + 4]);
+      const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
 
       // ---- running (stale) maximum: decide now, in registers; the accumulator itself is rescaled further down
       float sc = 1.0f;
@@ -200,7 +215,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         }
       }
       const float mc = m_used * c;
-      float rs0 = 0.f, rs1 = 0.f;
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent row-sum chains (latency, see above)
       // 64 keys -> 32 packed bf16x2 columns. 3 of every 8 exponentials run on the FMA pipe (exp2_fma), the rest on MUFU:
       // ncu showed the XU pipe at 61% with FMA at 17%, i.e. the kernel is MUFU-bound at head_dim 64.
       auto expo = [&](const uint32_t (&sa)[32], const uint32_t (&sb)[32], uint32_t (&pk)[32]) {
@@ -213,8 +228,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             const int e = (i >> 1) & 7;  // position within a group of 8 pairs
             const float p0 = (e == 1 || e == 4 || e == 6) ? exp2_fma(x0) : fast_exp2(x0);
             const float p1 = (e == 2 || e == 4 || e == 7) ? exp2_fma(x1) : fast_exp2(x1);
-            rs0 += p0;
-            rs1 += p1;
+            rs[(i >> 1) & 3] += p0;
+            rs[4 + ((i >> 1) & 3)] += p1;
             pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
           }
         }
@@ -241,7 +256,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       expo(s2, s3, pk);
       tmem_st32(tP + lane_off + 32, pk);
       tmem_st_wait();
-      l_run += rs0 + rs1;
+      l_run += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
       tc_fence_before();
       mbar_arrive(p_full);
     }

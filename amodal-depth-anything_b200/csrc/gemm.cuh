@@ -3,7 +3,10 @@
 //   warp 0      : TMA producer  (A and B tiles, 128-byte swizzle, 4..8 stage mbarrier ring)
 //   warp 1      : MMA issuer    (tcgen05.mma, 128 x BN x 16 per CTA, fp32 accumulators in TMEM, 2 accumulator stages)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem -> TMA store)
+//   warps 4..11 : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem -> TMA store);
+//                                 two warpgroups split the tile's 64-column groups: ncu showed the 4-warp epilogue
+//                                 latency-bound (issue 26%, XU 25%, tensor pipe 50% on the GELU GEMM), not pipe-bound.
+//                                 setmaxnreg moves registers from the producer/MMA warpgroup to the epilogue warpgroups.
 //
 // CG = 2 runs the kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x BN tile, each CTA
 // loads its own 128 rows of A but only HALF of the B tile, and the leader CTA issues one 256 x BN x 16 MMA that reads
@@ -35,7 +38,8 @@ constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kTileH = 8;     // conv mode: M tile = 8 x 16 pixels
 constexpr int kTileW = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiThreads = 256;   // warps 4..11
 
 enum EpiMode : int {
   EPI_BF16 = 0,       // out_bf16 = act((acc + bias) * gamma) [+ resid1 + resid2]; optional second copy with ReLU; TMA store
@@ -78,7 +82,7 @@ struct GemmCfg {
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
-  static constexpr int kStagingBytes = 4 * 2 * 4096;             // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int kStagingBytes = 8 * 4096;                 // 8 epilogue warps x one 32-row x 128 B buffer
   static constexpr int kVecBytes = 2 * 256 * 4;                  // bias + gamma of the current N tile
   static constexpr int kBarBytes = 256;
   // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1 KB aligned (checked)
@@ -144,7 +148,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp of every CTA in the pair
+      mbar_init(tempty_bar(s), 8 * CG);  // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
@@ -172,6 +176,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
   const int num_kb = (g.a_mode == A_CONV3X3) ? 9 * g.c_chunks : (g.K + kBlockK - 1) / kBlockK;
 
+  // Register rebalancing: the kernel is compiled for 168 regs/thread (384 threads); the producer/MMA warpgroup gives
+  // registers back and the two epilogue warpgroups take them (setmaxnreg must dominate each role's code for ptxas).
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
@@ -259,15 +267,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // epilogue warpgroup: takes every other 64-column group of the tile
     const int row = q * 32 + lane;     // accumulator row owned by this thread
-    const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
-    const uint32_t stg0 = staging_base + static_cast<uint32_t>(q) * 8192u;  // this warp's two 4 KB staging buffers
+    const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
+    const uint32_t buf = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;  // this warp's staging buffer
     const uint32_t st_row = static_cast<uint32_t>(lane) * 128u;
     const uint32_t st_sw = static_cast<uint32_t>(lane & 7);
-    int sbuf = 0;                      // staging buffer to use next
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool tma_out = (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU);
@@ -304,13 +314,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float* s_bias = s_vec;
       float* s_gamma = s_bias + 256;
       if (tma_out) {
-        named_bar_sync(1, 128);
-        for (int i = et; i < BN; i += 128) {
+        named_bar_sync(1, kEpiThreads);
+        for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;
           s_bias[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
           s_gamma[i] = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
       }
 
       mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
@@ -323,7 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int on0 = (g.epi == EPI_SWIGLU) ? (n0 >> 1) : n0;
           const int n_out = (g.epi == EPI_SWIGLU) ? (g.N >> 1) : g.N;
 #pragma unroll 1
-          for (int cg = 0; cg < out_cols / 64; ++cg) {
+          for (int cg = half; cg < out_cols / 64; cg += 2) {
             const int oc = on0 + cg * 64;  // first output column of this 64-wide group
             if (oc >= n_out) break;
             uint32_t pk[32];               // 64 bf16 outputs of this thread's row
@@ -385,8 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // ---- registers -> swizzled staging buffer -> TMA store
             const int passes = g.has_relu_copy ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
-              const uint32_t buf = stg0 + static_cast<uint32_t>(sbuf) * 4096u;
-              if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has drained it
+              if (lane == 0) bulk_wait_read<0>();  // the previous store has drained this warp's staging buffer
               __syncwarp();
               if (pass == 1) {
 #pragma unroll
@@ -411,12 +420,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   tma_store_2d(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
                 bulk_commit();
               }
-              sbuf ^= 1;
             }
           }
         }
       } else if (g.epi == EPI_TAIL) {
-        if constexpr (BN == 32) {
+        if constexpr (BN == 32) if (half == 0) {
           uint32_t r[32];
           tmem_ld32(t_addr, r);
           tmem_ld_wait();
@@ -433,7 +441,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else {
         // EPI_EMBED / EPI_CONVT: direct per-thread stores (one GEMM each per forward; row remap / pixel-shuffle scatter)
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_addr + c * 32, r);
           tmem_ld_wait();
