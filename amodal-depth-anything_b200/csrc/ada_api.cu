@@ -87,6 +87,11 @@ static void require_device() {
   if (!di.ok) throw AdaError(ADA_ENODEVICE, di.why);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launcher
 template <int BN, int CG>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
@@ -140,10 +145,6 @@ struct GemmLaunch {
   int force_cg = 0;          // 0 = auto, 1 = single CTA tiles, 2 = CTA pairs (cta_group::2)
 };
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 static int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
 
@@ -195,7 +196,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     static const int cg_env = env_int("ADA_GEMM_CG", 0);
     const int want = L.force_cg ? L.force_cg : cg_env;
     const int tiles_n_ = (L.N + bn - 1) / bn;
-    bool ok = bn >= 128 && g.epi != EPI_TAIL;
+    bool ok = (bn == 256 || (want == 2 && bn == 128)) && g.epi != EPI_TAIL;  // N=128 pairs are smem-read bound (A 4 KB + B 2 KB / 32 clk)
     if (ok && L.a_mode == A_CONV3X3) {
       const int pad1 = (L.W + kTileW - 1) / kTileW * kTileW, pad2 = (L.W + 2 * kTileW - 1) / (2 * kTileW) * 2 * kTileW;
       const long long pairs = static_cast<long long>(L.batch) * ((L.H + kTileH - 1) / kTileH) * (pad2 / (2 * kTileW)) * tiles_n_;
@@ -300,9 +301,13 @@ static void launch_layernorm(float* x, const __nv_bfloat16* delta, const float* 
 
 static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st) {
   static bool attr_set = false;
+  static int variant = 0;
   if (!attr_set) {
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kAttSmemBytes));
+    variant = env_int("ADA_ATT_VARIANT", 0);
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
   const int D = heads * 64;
@@ -310,6 +315,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
   uint32_t box[3] = {64, 128, 1};
   CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
+  uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
+  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
   AttArgs a;
   a.B = B;
   a.N = N;
@@ -319,7 +327,12 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-  attention_tcgen05_kernel<<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, a);
+  switch (variant) {
+    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 3: attention_tcgen05_kernel<3><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+  }
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }

@@ -35,8 +35,12 @@ struct AttArgs {
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
+// VARIANT is a bring-up / measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = all exponentials on MUFU,
+// 2 = exponentials replaced by a copy (timing skeleton only, wrong results), 3 = all exponentials on the FMA pipe.
+template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs a) {
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+                         const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
   const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152;
@@ -226,8 +230,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
             const float x0 = fmaf(__uint_as_float(h ? sb[i] : sa[i]), c, -mc);
             const float x1 = fmaf(__uint_as_float(h ? sb[i + 1] : sa[i + 1]), c, -mc);
             const int e = (i >> 1) & 7;  // position within a group of 8 pairs
-            const float p0 = (e == 1 || e == 4 || e == 6) ? exp2_fma(x0) : fast_exp2(x0);
-            const float p1 = (e == 2 || e == 4 || e == 7) ? exp2_fma(x1) : fast_exp2(x1);
+            float p0, p1;
+            if constexpr (VARIANT == 1) {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            } else if constexpr (VARIANT == 2) {
+              p0 = x0;
+              p1 = x1;
+            } else if constexpr (VARIANT == 3) {
+              p0 = exp2_fma(x0);
+              p1 = exp2_fma(x1);
+            } else {
+              p0 = (e == 1 || e == 4 || e == 6) ? exp2_fma(x0) : fast_exp2(x0);
+              p1 = (e == 2 || e == 4 || e == 7) ? exp2_fma(x1) : fast_exp2(x1);
+            }
+            (void)e;
             rs[(i >> 1) & 3] += p0;
             rs[4 + ((i >> 1) & 3)] += p1;
             pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
@@ -260,27 +277,34 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l -> bf16
+    // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile is dead once the last S MMA has retired) -> one TMA
+    //      store per CTA. Row-per-thread global stores touched 32 cache lines per warp instruction (ncu: 32 sectors/request).
     mbar_wait(o_full, (num_kv - 1) & 1, 0x580);
     tc_fence_after();
-    const int qi = q0 + row;
     const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = a.out + (static_cast<long long>(img) * a.N + min(qi, a.N - 1)) * a.D + head * kAttD;
+    const uint32_t o_row = sQ + static_cast<uint32_t>(row) * 128u;
+    const uint32_t o_sw = static_cast<uint32_t>(row & 7);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t r[32];
       tmem_ld32(tO + lane_off + h * 32, r);
       tmem_ld_wait();
-      if (qi < a.N) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + h * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
-                              pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
-                              pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
-                              pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
-        }
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t chunk = static_cast<uint32_t>(h * 4 + i);
+        st_shared_v4(o_row + ((chunk ^ o_sw) << 4),
+                     pack_bf16x2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
+                     pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
+                     pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
+                     pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
       }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {  // first softmax thread; rows past N are clipped by the tensor map
+      tma_store_3d(&tmap_out, sQ, head * kAttD, q0, img);
+      bulk_commit();
+      bulk_wait<0>();
     }
   }
 
