@@ -308,6 +308,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
   const int D = heads * 64;
@@ -331,6 +334,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
     case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 3: attention_tcgen05_kernel<3><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 4: attention_tcgen05_kernel<4><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 5: attention_tcgen05_kernel<5><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 6: attention_tcgen05_kernel<6><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
   }
   ADA_CHECK_CUDA(cudaGetLastError());

@@ -163,12 +163,37 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       tc_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld32(tS + lane_off, s0);
-      tmem_ld32(tS + lane_off + 32, s1);
-      tmem_ld32(tS + lane_off + 64, s2);
-      tmem_ld32(tS + lane_off + 96, s3);
-      tmem_ld_wait();
+      if constexpr (VARIANT == 4) {  // measurement: one TMEM load instead of four (skeleton + 1/4 of the TMEM read traffic)
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s1[i] = s0[i] ^ 1u;
+          s2[i] = s0[i] ^ 2u;
+          s3[i] = s0[i] ^ 3u;
+        }
+      } else {
+        tmem_ld32(tS + lane_off + 32, s1);
+        tmem_ld32(tS + lane_off + 64, s2);
+        tmem_ld32(tS + lane_off + 96, s3);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(s_free);  // S(j) now lives in registers
+      if constexpr (VARIANT == 5 || VARIANT == 6) {  // measurement: data movement + barriers + MMAs only
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1, 0x570);
+          tc_fence_after();
+        }
+        if constexpr (VARIANT == 5) {
+          tmem_st32(tP + lane_off, s0);
+          tmem_st32(tP + lane_off + 32, s1);
+          tmem_st_wait();
+        }
+        l_run = 1.0f;
+        tc_fence_before();
+        mbar_arrive(p_full);
+        continue;
+      }
       if (kv_valid < kAttKV) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -234,7 +259,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             if constexpr (VARIANT == 1) {
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
-            } else if constexpr (VARIANT == 2) {
+            } else if constexpr (VARIANT == 2 || VARIANT == 4) {
               p0 = x0;
               p1 = x1;
             } else if constexpr (VARIANT == 3) {
