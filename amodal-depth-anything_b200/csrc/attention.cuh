@@ -3,54 +3,58 @@
 // without materialising the N x N score matrix.
 //
 // One CTA = 128 queries of one (image, head); Q/K/V are read in place from the [B, N, 3, H, 64] QKV GEMM output
-// through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
-//   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
-//   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)  -> TMEM cols [0,128)
-//                                 O += P V   (128x64x128, P from TMEM, V MN-major from smem) -> TMEM cols [192,256)
-//   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane): the whole 128-wide score row is pulled into
-//                registers with four back-to-back tcgen05.ld (one wait), so row max / row sum need no shuffles and S is
-//                released to the MMA warp before the exponentials start (S(j+1) overlaps softmax(j)).
-//                P is written back to TMEM (cols [128,192), bf16 pairs) with tcgen05.st and consumed as the A operand
-//                of the P V MMA straight from there: shared memory only carries Q/K/V (its bandwidth, 128 B/clk, was
-//                the co-bottleneck when P went through a 32 KB swizzled smem tile).
-// The running output stays in TMEM across KV tiles (P V accumulates in place). Rows are kept relative to a *stale* maximum:
-// the accumulator is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row's maximum grows by more than 2^8,
-// which happens in the first tile or two; p may then reach 256, harmless in fp32/bf16, and O / l is exact either way.
-// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
-// The kernel is MUFU (ex2) bound at head_dim 64: 128x128 exponentials per tile = 1024 cycles/SM vs 512 cycles of MMA.
+// through 3-D TMA maps (out-of-range tokens are zero-filled by the hardware). KV tiles are 64 keys wide so that BOTH the
+// score tile and the probability tile can be double-buffered inside 256 TMEM columns (two CTAs per SM):
+//     S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
+//   warp 0     : TMA producer (Q once, then 4-stage K and V rings of 8 KB tiles)
+//   warp 1     : tcgen05 issuer.  S_b = Q K_j^T (128x64x64, K-major operands)      for tile j+2 while softmax works on j
+//                                 O  += P_b V_j  (128x64x64, P from TMEM, V MN-major from smem)
+//   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane): it pulls its 64 scores into registers
+//                (tcgen05.ld), releases the S buffer, exponentiates against a *stale* row maximum, writes bf16 P back to
+//                TMEM (tcgen05.st) and signals the issuer. Row max / row sum need no shuffles.
+// Why this shape: measured on the 128-key single-buffered version, the barrier round trip softmax -> issuer -> tensor
+// pipe -> softmax alone (no math at all) cost 0.233 ms of the 0.39 ms kernel; with S and P double-buffered the softmax
+// warps never wait on it. The accumulator stays in TMEM and is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when a
+// row maximum grows by more than 2^8 (first tile or two); p may reach 256, harmless in fp32/bf16, and O / l is exact.
+// The kernel is MUFU (ex2) / issue bound at head_dim 64: 128 x 128 exponentials per 128 keys = 1024 cycles per SM.
 #pragma once
 #include "ptx.cuh"
 
 namespace ada {
 
 constexpr int kAttThreads = 192;
-constexpr int kAttQ = 128, kAttKV = 128, kAttD = 64;
-constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 256 /*barriers*/;
+constexpr int kAttQ = 128, kAttKV = 64, kAttD = 64;
+constexpr int kAttStages = 4;
+constexpr int kAttTileBytes = kAttKV * kAttD * 2;  // 8 KB
+constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * kAttStages * kAttTileBytes /*K,V*/ + 256 /*barriers*/;
 constexpr int kAttTmemCols = 256;
 constexpr float kAttRescaleLog2 = 8.0f;  // rescale O only when a row max grows by more than 2^8
 
 struct AttArgs {
   int B, N, heads, D;        // D = heads * 64
-  __nv_bfloat16* out;        // [B*N, D]
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
-// VARIANT is a bring-up / measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = all exponentials on MUFU,
-// 2 = exponentials replaced by a copy (timing skeleton only, wrong results), 3 = all exponentials on the FMA pipe.
+// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 2 = exponentials replaced by a copy (timing skeleton
+// only, wrong results).
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                         const AttArgs a) {
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                         const __grid_constant__ CUtensorMap tmap_out, const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
-  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152;
-  const uint32_t bar = sbase + 81920;
-  const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24, s_free = bar + 32;
-  auto k_full = [&](int s) { return bar + 40 + 8u * s; };
-  auto k_empty = [&](int s) { return bar + 56 + 8u * s; };
-  auto v_full = [&](int s) { return bar + 72 + 8u * s; };
-  auto v_empty = [&](int s) { return bar + 88 + 8u * s; };
-  const uint32_t tmem_ptr_smem = bar + 104;
+  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sK + kAttStages * kAttTileBytes;
+  const uint32_t bar = sV + kAttStages * kAttTileBytes;
+  const uint32_t q_full = bar;
+  auto s_full = [&](int b) { return bar + 8 + 8u * b; };
+  auto s_free = [&](int b) { return bar + 24 + 8u * b; };
+  auto p_full = [&](int b) { return bar + 40 + 8u * b; };
+  auto pv_done = [&](int b) { return bar + 56 + 8u * b; };
+  auto k_full = [&](int s) { return bar + 72 + 8u * s; };
+  auto k_empty = [&](int s) { return bar + 104 + 8u * s; };
+  auto v_full = [&](int s) { return bar + 136 + 8u * s; };
+  auto v_empty = [&](int s) { return bar + 168 + 8u * s; };
+  const uint32_t tmem_ptr_smem = bar + 200;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAttQ, head = blockIdx.y, img = blockIdx.z;
@@ -61,13 +65,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       g_dev_error[0] = 0xA11;
       __trap();
     }
-    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    mbar_init(s_free, 128);
-    for (int s = 0; s < 2; ++s) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(s_free(b), 128);
+      mbar_init(p_full(b), 128);
+      mbar_init(pv_done(b), 1);
+    }
+    for (int s = 0; s < kAttStages; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1);
@@ -90,64 +97,66 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &tmap_qkv, q_full, head * kAttD, q0, img);
+      tma_load_3d(sQ, &tmap_q, q_full, head * kAttD, q0, img);
     }
     for (int j = 0; j < num_kv; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      const int s = j % kAttStages;
+      const uint32_t ph = (j / kAttStages) & 1;
       mbar_wait(k_empty(s), ph ^ 1u, 0x500 + s);
       if (lane == 0) {
-        mbar_expect_tx(k_full(s), 16384);
-        tma_load_3d(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
+        mbar_expect_tx(k_full(s), kAttTileBytes);
+        tma_load_3d(sK + s * kAttTileBytes, &tmap_kv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
       }
       mbar_wait(v_empty(s), ph ^ 1u, 0x510 + s);
       if (lane == 0) {
-        mbar_expect_tx(v_full(s), 16384);
-        tma_load_3d(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
+        mbar_expect_tx(v_full(s), kAttTileBytes);
+        tma_load_3d(sV + s * kAttTileBytes, &tmap_kv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
-    auto issue_s = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(k_full(s), (j >> 1) & 1, 0x520 + s);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, kAttKV, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, kAttD, 0, 1);  // B = V is MN-major (d contiguous)
+    auto issue_s = [&](int j) {  // S_{j&1} = Q K_j^T
+      const int s = j % kAttStages;
+      mbar_wait(k_full(s), (j / kAttStages) & 1, 0x520 + s);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t da = make_smem_desc_sw128(sQ + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sK + s * 16384 + k * 32, 16, 1024);
-          umma_bf16_ss(tS, da, db, idesc_s, k > 0 ? 1u : 0u);
+          const uint64_t db = make_smem_desc_sw128(sK + s * kAttTileBytes + k * 32, 16, 1024);
+          umma_bf16_ss(tS + (j & 1) * 64, da, db, idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(k_empty(s));
-        umma_commit(s_full);
+        umma_commit(s_full(j & 1));
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0, 0x530);
     issue_s(0);
+    if (num_kv > 1) issue_s(1);
     for (int j = 0; j < num_kv; ++j) {
-      const int s = j & 1;
-      if (j + 1 < num_kv) {
-        mbar_wait(s_free, j & 1, 0x535);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
-        issue_s(j + 1);
-      }
-      mbar_wait(p_full, j & 1, 0x540);    // P(j) in TMEM, O rescaled if needed
-      mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
+      const int b = j & 1, s = j % kAttStages;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(p_full(b), ph, 0x540 + b);  // P_b(j) in TMEM (and S_b(j) consumed, O rescaled if it had to be)
+      mbar_wait(v_full(s), (j / kAttStages) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
-          const uint64_t db = make_smem_desc_sw128(sV + s * 16384 + kk * 2048, 0, 1024);
-          umma_bf16_ts(tO, tP + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
+          const uint64_t db = make_smem_desc_sw128(sV + s * kAttTileBytes + kk * 2048, 0, 1024);
+          umma_bf16_ts(tO, tP + b * 32 + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(v_empty(s));
-        umma_commit(o_full);
+        umma_commit(pv_done(b));
       }
       __syncwarp();
+      if (j + 2 < num_kv) {
+        mbar_wait(s_free(b), ph, 0x535 + b);  // true by now (s_free precedes p_full); S_b may be overwritten
+        issue_s(j + 2);
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
@@ -158,59 +167,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     float m_used = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < num_kv; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
       const int kv_valid = min(kAttKV, a.N - j * kAttKV);
-      mbar_wait(s_full, j & 1, 0x560);
+      mbar_wait(s_full(b), ph, 0x560 + b);
       tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tS + lane_off, s0);
-      if constexpr (VARIANT == 4) {  // measurement: one TMEM load instead of four (skeleton + 1/4 of the TMEM read traffic)
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s1[i] = s0[i] ^ 1u;
-          s2[i] = s0[i] ^ 2u;
-          s3[i] = s0[i] ^ 3u;
-        }
-      } else {
-        tmem_ld32(tS + lane_off + 32, s1);
-        tmem_ld32(tS + lane_off + 64, s2);
-        tmem_ld32(tS + lane_off + 96, s3);
-        tmem_ld_wait();
-      }
+      uint32_t s0[32], s1[32];
+      tmem_ld32(tS + lane_off + b * 64, s0);
+      tmem_ld32(tS + lane_off + b * 64 + 32, s1);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);  // S(j) now lives in registers
-      if constexpr (VARIANT == 5 || VARIANT == 6) {  // measurement: data movement + barriers + MMAs only
-        if (j > 0) {
-          mbar_wait(o_full, (j - 1) & 1, 0x570);
-          tc_fence_after();
-        }
-        if constexpr (VARIANT == 5) {
-          tmem_st32(tP + lane_off, s0);
-          tmem_st32(tP + lane_off + 32, s1);
-          tmem_st_wait();
-        }
-        l_run = 1.0f;
-        tc_fence_before();
-        mbar_arrive(p_full);
-        continue;
-      }
+      mbar_arrive(s_free(b));  // S_b(j) now lives in registers -> the issuer may overwrite it with S(j+2)
       if (kv_valid < kAttKV) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= kv_valid) s0[i] = 0xff800000u;
           if (32 + i >= kv_valid) s1[i] = 0xff800000u;
-          if (64 + i >= kv_valid) s2[i] = 0xff800000u;
-          if (96 + i >= kv_valid) s3[i] = 0xff800000u;
         }
       }
-      // 16 independent max chains (a single chain of 128 dependent FMNMX would cost 128 x 4 cycles of pure latency)
-      float tm[16];
+      // 8 independent max chains
+      float tm[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         tm[i] = fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 4]));
         tm[4 + i] = fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 4]));
-        tm[8 + i] = fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 4]));
-        tm[12 + i] = fmaxf(__uint_as_float(s3[i]), __uint_as_float(s3[i + 4]));
       }
 #pragma unroll
       for (int i = 8; i < 32; i += 4) {
@@ -218,73 +198,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         for (int k = 0; k < 4; ++k) {
           tm[k] = fmaxf(tm[k], __uint_as_float(s0[i + k]));
           tm[4 + k] = fmaxf(tm[4 + k], __uint_as_float(s1[i + k]));
-          tm[8 + k] = fmaxf(tm[8 + k], __uint_as_float(s2[i + k]));
-          tm[12 + k] = fmaxf(tm[12 + k], __uint_as_float(s3[i + k]));
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tm[i] = fmaxf(tm[i], tm[i + 8]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) tm[i] = fmaxf(tm[i], tm[i + 4]);
       const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
 
-      // ---- running (stale) maximum: decide now, in registers; the accumulator itself is rescaled further down
-      float sc = 1.0f;
-      bool rescale = false;
+      // ---- running (stale) maximum
       if (j == 0) {
         m_used = tmax;
       } else {
         const bool grow = (tmax - m_used) * c > kAttRescaleLog2;
-        rescale = __any_sync(0xffffffffu, grow);  // rare (first tile or two)
-        if (rescale) {
+        if (__any_sync(0xffffffffu, grow)) {  // rare: bring this warp's 32 accumulator rows to the new maxima
           const float m_new = fmaxf(m_used, tmax);
-          sc = fast_exp2((m_used - m_new) * c);
+          const float sc = fast_exp2((m_used - m_new) * c);
           m_used = m_new;
           l_run *= sc;
-        }
-      }
-      const float mc = m_used * c;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent row-sum chains (latency, see above)
-      // 64 keys -> 32 packed bf16x2 columns. 3 of every 8 exponentials run on the FMA pipe (exp2_fma), the rest on MUFU:
-      // ncu showed the XU pipe at 61% with FMA at 17%, i.e. the kernel is MUFU-bound at head_dim 64.
-      auto expo = [&](const uint32_t (&sa)[32], const uint32_t (&sb)[32], uint32_t (&pk)[32]) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(h ? sb[i] : sa[i]), c, -mc);
-            const float x1 = fmaf(__uint_as_float(h ? sb[i + 1] : sa[i + 1]), c, -mc);
-            const int e = (i >> 1) & 7;  // position within a group of 8 pairs
-            float p0, p1;
-            if constexpr (VARIANT == 1) {
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            } else if constexpr (VARIANT == 2 || VARIANT == 4) {
-              p0 = x0;
-              p1 = x1;
-            } else if constexpr (VARIANT == 3) {
-              p0 = exp2_fma(x0);
-              p1 = exp2_fma(x1);
-            } else {
-              p0 = (e == 1 || e == 4 || e == 6) ? exp2_fma(x0) : fast_exp2(x0);
-              p1 = (e == 2 || e == 4 || e == 7) ? exp2_fma(x1) : fast_exp2(x1);
-            }
-            (void)e;
-            rs[(i >> 1) & 3] += p0;
-            rs[4 + ((i >> 1) & 3)] += p1;
-            pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-          }
-        }
-      };
-      uint32_t pk[32];
-      expo(s0, s1, pk);  // first half of the row before touching TMEM: hides the wait for P(j-1) V(j-1) below
-      // P(j-1) V(j-1) must have retired before P's TMEM columns are overwritten (and before O may be rescaled)
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1, 0x570);
-        tc_fence_after();
-        if (rescale) {  // bring this warp's 32 accumulator rows to the new maxima
+          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1, 0x570);  // every P V issued so far has retired
+          tc_fence_after();
 #pragma unroll 1
-          for (int h = 0; h < 8; ++h) {  // 8 columns at a time: this path is rare, keep its register footprint small
+          for (int h = 0; h < 8; ++h) {  // 8 columns at a time: keep the register footprint of this path small
             uint32_t r[8];
             tmem_ld8(tO + lane_off + h * 8, r);
             tmem_ld_wait();
@@ -292,19 +225,44 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
             tmem_st8(tO + lane_off + h * 8, r);
           }
+          tmem_st_wait();
         }
       }
-      tmem_st32(tP + lane_off, pk);
-      expo(s2, s3, pk);
-      tmem_st32(tP + lane_off + 32, pk);
-      tmem_st_wait();
+      const float mc = m_used * c;
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float x0 = fmaf(__uint_as_float(h ? s1[i] : s0[i]), c, -mc);
+          const float x1 = fmaf(__uint_as_float(h ? s1[i + 1] : s0[i + 1]), c, -mc);
+          float p0, p1;
+          if constexpr (VARIANT == 2) {
+            p0 = x0;
+            p1 = x1;
+          } else {
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+          }
+          rs[(i >> 1) & 3] += p0;
+          rs[4 + ((i >> 1) & 3)] += p1;
+          pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+        }
+      }
       l_run += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      if (j >= 2) {  // P_b was last read by P V (j-2)
+        mbar_wait(pv_done(b), ((j - 2) >> 1) & 1, 0x575 + b);
+        tc_fence_after();
+      }
+      tmem_st32(tP + lane_off + b * 32, pk);
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full(b));
     }
     // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile is dead once the last S MMA has retired) -> one TMA
-    //      store per CTA. Row-per-thread global stores touched 32 cache lines per warp instruction (ncu: 32 sectors/request).
-    mbar_wait(o_full, (num_kv - 1) & 1, 0x580);
+    //      store per CTA (row-per-thread global stores touch 32 cache lines per warp instruction).
+    mbar_wait(pv_done((num_kv - 1) & 1), ((num_kv - 1) >> 1) & 1, 0x580);
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const uint32_t o_row = sQ + static_cast<uint32_t>(row) * 128u;

@@ -296,13 +296,15 @@ def main():
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": cfg,
-            "e2e": {"value": gb / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
+            "e2e": {"value": gb / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
+                    "how": "StreamedInference: pinned host -> H2D -> AmodalDAv2.forward -> D2H per step, copies on a side stream"},
             "gpu_launches": launches * a.steps,
             "clocks": clocks,
             "roofline": roof,
-            "model_tflops": value * gf / 1e3 if gf else None,
-            "model_frac_of_peak": (value * gf / 1e3) / peaks["tf_sustained"] if gf else None,
+            "model_tflops_per_gpu": value * gf / 1e3 / world if gf else None,
+            "model_frac_of_peak": (value * gf / 1e3 / world) / peaks["tf_sustained"] if gf else None,
+            "model_frac_of_burst_peak": (value * gf / 1e3 / world) / peaks["tf_burst"] if gf else None,
             "breakdown": breakdown,
             "cpu_baseline": cpu_base,
             "workspace_gb": model.workspace_bytes() / 2 ** 30,
