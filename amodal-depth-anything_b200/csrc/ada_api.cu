@@ -305,30 +305,31 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
-  uint32_t box_q[3] = {64, kAttQ, 1}, box_kv[3] = {64, kAttKV, 1};
-  CUtensorMap tmq = make_tmap_bf16(qkv, 3, dims, str, box_q);
-  CUtensorMap tmkv = make_tmap_bf16(qkv, 3, dims, str, box_kv);
+  uint32_t box[3] = {64, 128, 1};
+  CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
   uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
-  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box_q);
+  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
   AttArgs a;
   a.B = B;
   a.N = N;
   a.heads = heads;
   a.D = D;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
-  dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
+  dim3 grid((N + 2 * kAttQ - 1) / (2 * kAttQ), heads, B);  // 256 queries (two tiles) per CTA
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-  if (variant == 2)
-    attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
-  else
-    attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
+  switch (variant) {
+    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+  }
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
