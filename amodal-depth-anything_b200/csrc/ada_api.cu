@@ -305,7 +305,6 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
@@ -323,10 +322,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.heads = heads;
   a.D = D;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
-  dim3 grid((N + 2 * kAttQ - 1) / (2 * kAttQ), heads, B);  // 256 queries (two tiles) per CTA
+  dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
   switch (variant) {
-    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
   }
