@@ -100,6 +100,9 @@ SIGNATURES = {
     "ada_op_patch_gather": (c_int32, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int32, c_int32,
                                       c_int32, c_int32, c_void_p]),
     "ada_op_im2col_s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ada_op_tail_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_void_p]),
+    "ada_pack_tail_taps": (c_int32, [c_void_p, c_int32, c_void_p]),
     "ada_pack_conv3x3": (c_int32, [c_void_p, c_int32, c_int32, c_void_p]),
     "ada_pack_convT": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
 }

@@ -362,6 +362,21 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
   ++g_launches;
 }
 
+static void launch_tail_gather(const __nv_bfloat16* V, const float* bias2, const float* aux, float* out, int B, int Hl,
+                               int Wl, int H, int W, int sigmoid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(tail_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((W + kTailTile - 1) / kTailTile, (H + kTailTile - 1) / kTailTile, B);
+  ProfScope prof(PC_UPSAMPLE, 2.0 * B * static_cast<double>(H) * W * 36.0 * 32.0,
+                 static_cast<double>(B) * (2.0 * Hl * Wl * kTailCh + 4.0 * H * W), st);
+  tail_gather_kernel<<<grid, 256, kTailSmemBytes, st>>>(V, bias2, aux, out, Hl, Wl, H, W, sigmoid);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
 static void launch_patch_gather(const float* rgb, const float* const* guides, const int* guide_ch, int n_guides,
                                 __nv_bfloat16* out, int B, int H, int W, int Kpad, cudaStream_t st) {
   ADA_REQUIRE(n_guides >= 0 && n_guides <= 3, "at most 3 guide tensors");
@@ -411,6 +426,14 @@ static std::vector<uint16_t> pack_convT_host(const float* w, int Cin, int Cout, 
     for (int co = 0; co < Cout; ++co)
       for (int kk = 0; kk < ks * ks; ++kk)
         o[(static_cast<size_t>(kk) * Cout + co) * Cin + ci] = f2bf(w[(static_cast<size_t>(ci) * Cout + co) * ks * ks + kk]);
+  return o;
+}
+// output_conv2.0 weight [32, Cm, 3, 3] -> per-tap 1x1 contractions [(tap*32 + co), Cm] for the fused tail
+static std::vector<uint16_t> pack_tail_taps_host(const float* w, int Cm) {
+  std::vector<uint16_t> o(static_cast<size_t>(288) * Cm);
+  for (int co = 0; co < 32; ++co)
+    for (int ci = 0; ci < Cm; ++ci)
+      for (int t = 0; t < 9; ++t) o[(static_cast<size_t>(t) * 32 + co) * Cm + ci] = f2bf(w[(static_cast<size_t>(co) * Cm + ci) * 9 + t]);
   return o;
 }
 static std::vector<uint16_t> to_bf16_host(const float* w, size_t n) {
@@ -520,6 +543,7 @@ struct ada_model {
   ConvW rn[4];
   RefineW ref[5];  // 1..4
   ConvW oc1, oc2;
+  __nv_bfloat16* w_tail_taps = nullptr;  // [288, F/2]
   float* tail_aux = nullptr;  // 32 weights + 1 bias of output_conv2.2
 
   // per-(H,W) position cache on device
@@ -541,7 +565,7 @@ struct ada_model {
   float* tokens_dbg = nullptr;
   __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *col4 = nullptr, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
   __nv_bfloat16 *t1 = nullptr, *sum = nullptr, *sumr = nullptr, *r2 = nullptr, *ocb = nullptr, *path[5] = {},
-                *oc1b = nullptr, *up = nullptr;
+                *oc1b = nullptr, *up = nullptr, *vtap = nullptr;
   int last_B = 0, last_H = 0, last_W = 0, last_launches = 0;
 
   ~ada_model() {
@@ -705,6 +729,11 @@ static void finalize_model(ada_model* m) {
     w.bout = up_f32(m, r + "out_conv.bias", {F});
   }
   m->oc1 = up_conv3x3(m, hd + "scratch.output_conv1", F / 2, F, true);
+  {
+    const HostTensor& t = need(m, hd + "scratch.output_conv2.0.weight", {32, F / 2, 3, 3});
+    std::vector<uint16_t> h = pack_tail_taps_host(t.data.data(), F / 2);
+    m->w_tail_taps = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+  }
   m->oc2 = up_conv3x3(m, hd + "scratch.output_conv2.0", 32, F / 2, true);
   {
     const HostTensor& w2 = need(m, hd + "scratch.output_conv2.2.weight", {1, 32, 1, 1});
@@ -811,6 +840,7 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
   }
   m->oc1b = b.take<__nv_bfloat16>(static_cast<size_t>(B) * ph[1] * pw[1] * (F / 2));
   m->up = b.take<__nv_bfloat16>(static_cast<size_t>(B) * H * W * (F / 2));
+  m->vtap = b.take<__nv_bfloat16>(static_cast<size_t>(B) * ph[1] * pw[1] * 288);
   return b.off + 1024;
 }
 
@@ -1045,8 +1075,16 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
   }
   // output_conv1 -> bilinear to (H, W) -> output_conv2 (conv3x3 + ReLU + 1x1 + Sigmoid) (dpt.py:193-195)
   conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st);
-  launch_upsample(m->oc1b, m->up, B, ph[1], pw[1], H, W, F / 2, st);
-  {
+  static const int tail_mode = env_int("ADA_TAIL", 1);  // 1 = fused (tap GEMM at low res + gather), 0 = upsample + implicit GEMM
+  if (tail_mode == 1 && ph[1] * 14 == H * 8 && pw[1] * 14 == W * 8) {
+    GemmArgs e{};
+    e.epi = EPI_BF16;
+    e.out_bf16 = m->vtap;
+    e.ldo = 288;
+    linear(m->oc1b, B * ph[1] * pw[1], F / 2, F / 2, m->w_tail_taps, 288, F / 2, e, st);
+    launch_tail_gather(m->vtap, m->oc2.b, m->tail_aux, out, B, ph[1], pw[1], H, W, c.sigmoid, st);
+  } else {
+    launch_upsample(m->oc1b, m->up, B, ph[1], pw[1], H, W, F / 2, st);
     GemmLaunch L;
     L.A = m->up;
     L.Bw = m->oc2.w;
@@ -1354,6 +1392,23 @@ int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, 
     require_device();
     launch_im2col_s2(static_cast<const __nv_bfloat16*>(in_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, H, W, C,
                      static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_tail_gather(const void* v_bf16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
+                       int32_t H, int32_t W, int32_t sigmoid, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_tail_gather(static_cast<const __nv_bfloat16*>(v_bf16), bias2, aux, out, B, Hl, Wl, H, W, sigmoid,
+                       static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_pack_tail_taps(const float* w_host, int32_t Cm, void* dst) {
+  return guarded([&] {
+    require_device();
+    std::vector<uint16_t> h = pack_tail_taps_host(w_host, Cm);
+    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   });
 }
 

@@ -236,4 +236,111 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
   *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused tail of the DPT head (dpt.py:194-195): bilinear 8h -> 14h upsample (align_corners=True) of the output_conv1 map,
+// output_conv2 = conv3x3(F/2 -> 32) + ReLU + conv1x1(32 -> 1) + Sigmoid.
+// A 1x1 channel contraction commutes with bilinear resampling, and a 3x3 conv is a sum over taps of shifted 1x1
+// contractions, so the 32 x (F/2) contraction of EACH tap is applied at LOW resolution by a tcgen05 GEMM
+// (V[pix, tap*32 + co] = sum_ci W2[co, ci, tap] * y[pix, ci]; 3x fewer FLOPs than the conv at 14h x 14h) and this kernel
+// finishes the job: out(p) = sigmoid(w3 . relu(b2 + sum_taps bilinear(V_tap)(p + d_tap)) + b3), taps that fall outside
+// the image contribute zero (the conv's zero padding). The 128-channel 14h x 14h map (2.2 GB at batch 32, re-read 9x
+// through L2 by the implicit-GEMM tail, which ran at 200 TFLOP/s) is never materialised.
+// One CTA = 16 x 16 output pixels; the <= 12 x 12 low-resolution patch of V (288 channels) it needs is staged in shared
+// memory once. Index math mirrors ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0+(i0<in-1).
+constexpr int kTailTile = 16;
+constexpr int kTailPatch = 12;
+constexpr int kTailCh = 288;  // 9 taps x 32
+constexpr int kTailSmemBytes = kTailPatch * kTailPatch * kTailCh * 2;
+
+__global__ void __launch_bounds__(256)
+tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict__ bias2, const float* __restrict__ aux,
+                   float* __restrict__ out, int Hl, int Wl, int H, int W, int apply_sigmoid) {
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * kTailTile, X0 = blockIdx.x * kTailTile;
+  const float sh = (H > 1) ? static_cast<float>(Hl - 1) / static_cast<float>(H - 1) : 0.f;
+  const float sw = (W > 1) ? static_cast<float>(Wl - 1) / static_cast<float>(W - 1) : 0.f;
+  // low-resolution patch covering every tap position of this tile
+  const int r0 = static_cast<int>(sh * max(Y0 - 1, 0));
+  const int r1 = min(static_cast<int>(sh * min(Y0 + kTailTile, H - 1)) + 1, Hl - 1);
+  const int c0 = static_cast<int>(sw * max(X0 - 1, 0));
+  const int c1 = min(static_cast<int>(sw * min(X0 + kTailTile, W - 1)) + 1, Wl - 1);
+  const int nrows = r1 - r0 + 1, ncols = c1 - c0 + 1;
+  if (nrows > kTailPatch || ncols > kTailPatch) {  // geometry other than 8h -> 14h: fail loudly
+    if (tid == 0) g_dev_error[0] = 0x7A11;
+    __trap();
+  }
+  {
+    const int total = nrows * ncols * (kTailCh / 8);
+    const uint4* src = reinterpret_cast<const uint4*>(V);
+    uint4* dst = reinterpret_cast<uint4*>(tail_smem);
+    for (int i = tid; i < total; i += 256) {
+      const int pix = i / (kTailCh / 8), q = i - pix * (kTailCh / 8);
+      const int r = pix / ncols, c = pix - r * ncols;
+      dst[i] = __ldg(src + ((static_cast<long long>(b) * Hl + r0 + r) * Wl + c0 + c) * (kTailCh / 8) + q);
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  const int Y = Y0 + ty, X = X0 + tx;
+  if (Y >= H || X >= W) return;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = __ldg(bias2 + i);
+  // per-tap source columns (three of them), rows handled in the loop
+  int xo0[3], xo1[3];
+  float lxv[3];
+  bool xok[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const int px = X + kx - 1;
+    xok[kx] = (px >= 0) && (px < W);
+    const float fx = sw * (xok[kx] ? px : 0);
+    const int x0 = static_cast<int>(fx);
+    xo0[kx] = x0 - c0;
+    xo1[kx] = x0 + (x0 < Wl - 1 ? 1 : 0) - c0;
+    lxv[kx] = fx - x0;
+  }
+#pragma unroll 1
+  for (int ky = 0; ky < 3; ++ky) {
+    const int py = Y + ky - 1;
+    if (py < 0 || py >= H) continue;
+    const float fy = sh * py;
+    const int y0 = static_cast<int>(fy);
+    const int yr0 = y0 - r0, yr1 = y0 + (y0 < Hl - 1 ? 1 : 0) - r0;
+    const float ly = fy - y0, hy = 1.f - ly;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      if (!xok[kx]) continue;
+      const float lx = lxv[kx], hx = 1.f - lx;
+      const int tap = ky * 3 + kx;
+      const float wgt[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+      const int pidx[4] = {yr0 * ncols + xo0[kx], yr0 * ncols + xo1[kx], yr1 * ncols + xo0[kx], yr1 * ncols + xo1[kx]};
+#pragma unroll
+      for (int cnr = 0; cnr < 4; ++cnr) {
+        const uint4* p = reinterpret_cast<const uint4*>(tail_smem + (pidx[cnr] * kTailCh + tap * 32) * 2);
+        const float wv = wgt[cnr];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 v = p[q];
+          acc[q * 8 + 0] = fmaf(wv, bf16_lo(v.x), acc[q * 8 + 0]);
+          acc[q * 8 + 1] = fmaf(wv, bf16_hi(v.x), acc[q * 8 + 1]);
+          acc[q * 8 + 2] = fmaf(wv, bf16_lo(v.y), acc[q * 8 + 2]);
+          acc[q * 8 + 3] = fmaf(wv, bf16_hi(v.y), acc[q * 8 + 3]);
+          acc[q * 8 + 4] = fmaf(wv, bf16_lo(v.z), acc[q * 8 + 4]);
+          acc[q * 8 + 5] = fmaf(wv, bf16_hi(v.z), acc[q * 8 + 5]);
+          acc[q * 8 + 6] = fmaf(wv, bf16_lo(v.w), acc[q * 8 + 6]);
+          acc[q * 8 + 7] = fmaf(wv, bf16_hi(v.w), acc[q * 8 + 7]);
+        }
+      }
+    }
+  }
+  float sres = __ldg(aux + 32);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sres = fmaf(fmaxf(acc[i], 0.f), __ldg(aux + i), sres);
+  if (apply_sigmoid) sres = 1.0f / (1.0f + __expf(-sres));
+  out[(static_cast<long long>(b) * H + Y) * W + X] = sres;
+}
+
 }  // namespace ada

@@ -111,3 +111,20 @@ def pack_convT(w, ks):
     out = torch.empty(ks * ks * Cout, Cin, dtype=torch.bfloat16, device="cuda")
     L.check(L.load().ada_pack_convT(_p(wh), Cin, Cout, ks, _p(out)))
     return out
+
+
+def pack_tail_taps(w):
+    """output_conv2.0 weight [32,Cm,3,3] -> per-tap 1x1 contractions, bf16 [288, Cm] on cuda."""
+    Cm = w.shape[1]
+    wh = w.detach().float().cpu().contiguous()
+    out = torch.empty(288, Cm, dtype=torch.bfloat16, device="cuda")
+    L.check(L.load().ada_pack_tail_taps(_p(wh), Cm, _p(out)))
+    return out
+
+
+def tail_gather(V, bias2, aux, H, W, sigmoid=True):
+    """V: NHWC bf16 [B,Hl,Wl,288] -> fp32 [B,H,W]."""
+    B, Hl, Wl, _ = V.shape
+    out = torch.empty(B, H, W, dtype=torch.float32, device=V.device)
+    L.check(L.load().ada_op_tail_gather(_p(V), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, int(sigmoid), _stream()))
+    return out

@@ -127,6 +127,13 @@ int ada_op_patch_gather(const float* rgb, const float* const* guides, const int3
                         void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t Kpad, void* stream);
 /* stride-2 3x3 gather for resize_layers[3] (dpt.py:102-107): NHWC -> [B*Ho*Wo, 9*C]. */
 int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* Fused tail (dpt.py:194-195): V = per-tap 1x1 contractions of output_conv2.0 applied to the low-res output_conv1 map,
+ * NHWC bf16 [B,Hl,Wl,288]; out[b,y,x] = sigmoid(w3 . relu(b2 + sum_taps bilinear_align_corners(V_tap)(y+dy, x+dx)) + b3),
+ * aux = [w3 (32), b3]. Requires the 8h -> 14h geometry (Hl*14 == H*8). */
+int ada_op_tail_gather(const void* v_bf16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
+                       int32_t H, int32_t W, int32_t sigmoid, void* stream);
+/* output_conv2.0 weight [32,Cm,3,3] (host fp32) -> [(tap*32+co), Cm] bf16 on the device. */
+int ada_pack_tail_taps(const float* w_host, int32_t Cm, void* dst_dev_bf16);
 /* Weight packers (host fp32 in, device bf16 out) -- the same code ada_finalize uses. */
 int ada_pack_conv3x3(const float* w_host, int32_t Cout, int32_t Cin, void* dst_dev_bf16 /* [Cout, 9*round_up(Cin,64)] */);
 int ada_pack_convT(const float* w_host, int32_t Cin, int32_t Cout, int32_t ks, void* dst_dev_bf16 /* [ks*ks*Cout, Cin] */);

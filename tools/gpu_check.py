@@ -219,6 +219,29 @@ def chk_upsample(Hi, Ho):
     return _cmp("up", out.permute(0, 3, 1, 2), ref, 2e-2, 1e-2)
 
 
+def chk_fused_tail(gh, gw):
+    """tap GEMM at low res + gather == conv2(interp(y)) chain of dpt.py:194-195."""
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(17)
+    B, Cm = 2, 64
+    Hl, Wl, H, W = 8 * gh, 8 * gw, 14 * gh, 14 * gw
+    y = torch.randn(B, Cm, Hl, Wl, generator=g, device="cuda").bfloat16()
+    w2 = torch.randn(32, Cm, 3, 3, generator=g, device="cuda") * (1.0 / (3 * Cm ** 0.5))
+    b2 = torch.randn(32, generator=g, device="cuda") * 0.1
+    w3 = torch.randn(32, generator=g, device="cuda") * 0.3
+    b3 = torch.randn(1, generator=g, device="cuda") * 0.1
+    up = torch.nn.functional.interpolate(y.float(), (H, W), mode="bilinear", align_corners=True)
+    z = torch.relu(torch.nn.functional.conv2d(up, w2.bfloat16().float(), b2, padding=1))
+    ref = torch.sigmoid((z * w3.view(1, 32, 1, 1)).sum(1) + b3)
+    wt = ops.pack_tail_taps(w2)
+    ya = y.permute(0, 2, 3, 1).reshape(B * Hl * Wl, Cm).contiguous()
+    V = torch.zeros(B, Hl, Wl, 288, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(ya, wt, out_bf16=V, ldo=288)
+    out = ops.tail_gather(V, b2, torch.cat([w3, b3]).contiguous(), H, W, True)
+    torch.cuda.synchronize()
+    return _cmp("fused_tail", out, ref, 5e-3, 0)
+
+
 def chk_patch_gather():
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(9)
@@ -288,6 +311,8 @@ CHECKS = {
     "channel_ln_1024": lambda: chk_channel_ln(1024),
     "upsample_19_37": lambda: chk_upsample(19, 37),
     "upsample_37_74": lambda: chk_upsample(37, 74),
+    "fused_tail_5x7": lambda: chk_fused_tail(5, 7),
+    "fused_tail_9x9": lambda: chk_fused_tail(9, 9),
     "patch_gather": chk_patch_gather,
     "im2col_s2": chk_im2col,
 }
