@@ -184,6 +184,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   g.K = L.K;
   g.a_mode = L.a_mode;
   int bn = L.force_bn ? L.force_bn : pick_bn(g.epi == EPI_SWIGLU ? std::max(L.N, 64) : L.N);
+  if (!L.force_bn && L.a_mode == A_LINEAR && L.K <= 256 && L.N > 64 && bn < 128) bn = 128;  // store-bound: fewer, wider tiles
   if (g.epi == EPI_TAIL) bn = 32;
   if (g.epi == EPI_SWIGLU && bn < 128) bn = 128;
   ADA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "bad BN");
@@ -306,6 +307,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
   const int D = heads * 64;
@@ -326,6 +328,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
   switch (variant) {
     case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
   }
   ADA_CHECK_CUDA(cudaGetLastError());

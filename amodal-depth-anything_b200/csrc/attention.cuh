@@ -101,13 +101,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(k_empty(s), ph ^ 1u, 0x500 + s);
       if (lane == 0) {
-        mbar_expect_tx(k_full(s), 16384);
-        tma_load_3d(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
+        if (VARIANT == 9 && j >= 2) {
+          mbar_arrive(k_full(s));  // measurement: reuse the resident tile, no L2 -> SM traffic
+        } else {
+          mbar_expect_tx(k_full(s), 16384);
+          tma_load_3d(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
+        }
       }
       mbar_wait(v_empty(s), ph ^ 1u, 0x510 + s);
       if (lane == 0) {
-        mbar_expect_tx(v_full(s), 16384);
-        tma_load_3d(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
+        if (VARIANT == 9 && j >= 2) {
+          mbar_arrive(v_full(s));
+        } else {
+          mbar_expect_tx(v_full(s), 16384);
+          tma_load_3d(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
+        }
       }
       __syncwarp();
     }
@@ -136,10 +144,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     for (int j = 0; j < num_kv; ++j) {
       const int s = j & 1;
       if (j + 1 < num_kv) {
-        mbar_wait(s_free, j & 1, 0x535);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
+        named_bar_sync(6, kAttSoftmaxThreads + 32);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
         issue_s(j + 1);
       }
-      mbar_wait(p_full, j & 1, 0x540);    // P(j) in TMEM, O rescaled if needed
+      named_bar_sync(7, kAttSoftmaxThreads + 32);  // P(j) in TMEM, O rescaled if needed
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
@@ -171,7 +179,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       tmem_ld32(tS + lane_off + half * 64 + 32, s1);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);  // this thread's part of S(j) now lives in registers
+      // this thread's part of S(j) now lives in registers. Hardware named barriers (arrive here, sync in the issuer warp)
+      // hand off in tens of cycles; the mbarrier round trip they replace cost ~350 cycles per hop and made the kernel
+      // synchronisation-latency bound (skeleton 0.23 ms of 0.39 ms with all math removed).
+      if (j + 1 < num_kv) named_bar_arrive(6, kAttSoftmaxThreads + 32);
       if (kv_valid < 64) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -227,7 +238,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           const float x0 = fmaf(__uint_as_float(h ? s1[i] : s0[i]), c, -mc);
           const float x1 = fmaf(__uint_as_float(h ? s1[i + 1] : s0[i + 1]), c, -mc);
           float p0, p1;
-          if constexpr (VARIANT == 2) {
+          if constexpr (VARIANT == 2 || VARIANT == 9) {
             p0 = x0;
             p1 = x1;
           } else {
@@ -258,7 +269,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       tmem_st32(tP + lane_off + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      named_bar_arrive(7, kAttSoftmaxThreads + 32);
     }
     // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile is dead once the last S MMA has retired) -> one TMA
     //      store per CTA (row-per-thread global stores touch 32 cache lines per warp instruction).

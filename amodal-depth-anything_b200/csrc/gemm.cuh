@@ -78,11 +78,15 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CG;                         // B rows (N) loaded by one CTA
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesFit = (232448 - 4 * 2 * 4096 - 2 * 256 * 4 - 256) / kStageBytes;
+  // epilogue staging: one 4 KB buffer per epilogue warp for the 256-wide tiles (two 64-column groups per warp and a long
+  // main loop hide the TMA-store drain), two for narrower tiles (small-K, store-bound GEMMs: a single buffer made every
+  // tile wait ~1 us for the previous store to release it)
+  static constexpr int kStgBufs = (BN == 256) ? 1 : 2;
+  static constexpr int kStagesFit = (232448 - 8 * kStgBufs * 4096 - 2 * 256 * 4 - 256) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
-  static constexpr int kStagingBytes = 8 * 4096;                 // 8 epilogue warps x one 32-row x 128 B buffer
+  static constexpr int kStagingBytes = 8 * kStgBufs * 4096;      // 8 epilogue warps x kStgBufs x (32 rows x 128 B)
   static constexpr int kVecBytes = 2 * 256 * 4;                  // bias + gamma of the current N tile
   static constexpr int kBarBytes = 256;
   // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1 KB aligned (checked)
@@ -275,7 +279,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 4) >> 2;  // epilogue warpgroup: takes every other 64-column group of the tile
     const int row = q * 32 + lane;     // accumulator row owned by this thread
     const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
-    const uint32_t buf = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;  // this warp's staging buffer
+    const uint32_t buf0 = staging_base + static_cast<uint32_t>(warp - 4) * (4096u * Cfg::kStgBufs);  // this warp's staging
+    int sbuf = 0;
     const uint32_t st_row = static_cast<uint32_t>(lane) * 128u;
     const uint32_t st_sw = static_cast<uint32_t>(lane & 7);
     int acc = 0;
@@ -395,7 +400,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // ---- registers -> swizzled staging buffer -> TMA store
             const int passes = g.has_relu_copy ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
-              if (lane == 0) bulk_wait_read<0>();  // the previous store has drained this warp's staging buffer
+              const uint32_t buf = buf0 + static_cast<uint32_t>(sbuf) * 4096u;
+              if (lane == 0) bulk_wait_read<Cfg::kStgBufs - 1>();  // the store that last used this buffer has drained it
               __syncwarp();
               if (pass == 1) {
 #pragma unroll
@@ -420,6 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   tma_store_2d(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
                 bulk_commit();
               }
+              if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
             }
           }
         }
