@@ -90,6 +90,7 @@ SIGNATURES = {
     "ada_destroy": (None, [c_void_p]),
     "ada_last_error": (c_char_p, []),
     "ada_device_error": (c_int32, [POINTER(c_uint32 * 4)]),
+    "ada_debug_timeline": (c_int32, [POINTER(ctypes.c_longlong), c_int32]),
     "ada_interp_pos_embed_host": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "ada_op_gemm": (c_int32, [POINTER(GemmDesc), c_void_p]),
     "ada_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32,

@@ -306,8 +306,10 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
     attr_set = true;
   }
   const int D = heads * 64;
@@ -327,8 +329,10 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
   switch (variant) {
+    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 10: attention_tcgen05_kernel<10><<<grid, kAttThreads, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0), st>>>(tm, tmo, a); break;
     default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
   }
   ADA_CHECK_CUDA(cudaGetLastError());
@@ -1140,6 +1144,14 @@ static int guarded(F&& f) {
 extern "C" {
 
 const char* ada_last_error(void) { return g_last_error.c_str(); }
+
+int ada_debug_timeline(long long* out, int32_t n) {
+  return guarded([&] {
+    ADA_REQUIRE(out && n > 0 && n <= 512, "bad argument");
+    ADA_CHECK_CUDA(cudaDeviceSynchronize());
+    ADA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_dev_timeline, sizeof(long long) * n));
+  });
+}
 
 int ada_device_error(uint32_t out[4]) {
   return guarded([&] { ADA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_dev_error, 16)); });

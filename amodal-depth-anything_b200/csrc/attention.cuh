@@ -38,8 +38,8 @@ struct AttArgs {
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
-// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 2 = exponentials replaced by a copy (timing skeleton
-// only, wrong results).
+// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = every exponential on MUFU, 2 = exponentials
+// replaced by a copy (timing skeleton only, wrong results), 9 = 2 + no K/V reloads, 10 = clock64 timeline of one thread.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
@@ -170,14 +170,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     const float c = a.scale_log2e;
     float m_used = -INFINITY, l_part = 0.f;
 
+    const bool tl = (VARIANT == 10) && threadIdx.x == 64 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
+    auto stamp = [&](int j, int k) {
+      if (tl) g_dev_timeline[j * 8 + k] = clock64();
+    };
     for (int j = 0; j < num_kv; ++j) {
       const int kv_valid = min(kAttKV, a.N - j * kAttKV) - half * 64;  // valid keys inside this thread's 64 columns
+      stamp(j, 0);
       mbar_wait(s_full, j & 1, 0x560);
+      stamp(j, 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld32(tS + lane_off + half * 64, s0);
       tmem_ld32(tS + lane_off + half * 64 + 32, s1);
       tmem_ld_wait();
+      stamp(j, 2);
       tc_fence_before();
       // this thread's part of S(j) now lives in registers. Hardware named barriers (arrive here, sync in the issuer warp)
       // hand off in tens of cycles; the mbarrier round trip they replace cost ~350 cycles per hop and made the kernel
@@ -212,6 +219,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       xm[half * 128 + row] = tmax;
       named_bar_sync(1 + qd, 64);
       tmax = fmaxf(tmax, xm[(half ^ 1) * 128 + row]);
+      stamp(j, 3);
 
       // ---- running (stale) maximum: both owners take the same decision from the same combined maximum
       float sc = 1.0f;
@@ -241,9 +249,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           if constexpr (VARIANT == 2 || VARIANT == 9) {
             p0 = x0;
             p1 = x1;
-          } else {
+          } else if constexpr (VARIANT == 1) {
             p0 = fast_exp2(x0);
             p1 = fast_exp2(x1);
+          } else {
+            // The exponentials are MUFU bound (clock64 timeline: 64 ex2 per thread take ~1235 cycles with two warps per
+            // scheduler = 1024 cycles of MUFU pipe). One pair in four goes to the FMA pipe instead; more than that and
+            // the extra ~9 instructions per element make the schedulers issue bound (measured: 3/8 gave no gain).
+            if (((i >> 1) & 3) == 3) {
+              p0 = exp2_fma(x0);
+              p1 = exp2_fma(x1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
           }
           rs[(i >> 1) & 3] += p0;
           rs[4 + ((i >> 1) & 3)] += p1;
@@ -251,6 +270,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         }
       }
       l_part += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      stamp(j, 4);
       if (j > 0) {  // P(j-1) V(j-1) must have retired before P is overwritten / O may be rescaled
         mbar_wait(o_full, (j - 1) & 1, 0x570);
         tc_fence_after();
@@ -266,8 +286,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           }
         }
       }
+      stamp(j, 5);
       tmem_st32(tP + lane_off + half * 32, pk);
       tmem_st_wait();
+      stamp(j, 6);
       tc_fence_before();
       named_bar_arrive(7, kAttSoftmaxThreads + 32);
     }

@@ -250,7 +250,8 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
 constexpr int kTailTile = 16;
 constexpr int kTailPatch = 12;
 constexpr int kTailCh = 288;  // 9 taps x 32
-constexpr int kTailSmemBytes = kTailPatch * kTailPatch * kTailCh * 2;
+constexpr int kTailPitch = kTailCh * 2 + 16;  // 592 B per low-res pixel: +16 B skews neighbouring pixels across all banks
+constexpr int kTailSmemBytes = kTailPatch * kTailPatch * kTailPitch;
 
 __global__ void __launch_bounds__(256)
 tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict__ bias2, const float* __restrict__ aux,
@@ -274,11 +275,11 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
   {
     const int total = nrows * ncols * (kTailCh / 8);
     const uint4* src = reinterpret_cast<const uint4*>(V);
-    uint4* dst = reinterpret_cast<uint4*>(tail_smem);
     for (int i = tid; i < total; i += 256) {
       const int pix = i / (kTailCh / 8), q = i - pix * (kTailCh / 8);
       const int r = pix / ncols, c = pix - r * ncols;
-      dst[i] = __ldg(src + ((static_cast<long long>(b) * Hl + r0 + r) * Wl + c0 + c) * (kTailCh / 8) + q);
+      *reinterpret_cast<uint4*>(tail_smem + pix * kTailPitch + q * 16) =
+          __ldg(src + ((static_cast<long long>(b) * Hl + r0 + r) * Wl + c0 + c) * (kTailCh / 8) + q);
     }
   }
   __syncthreads();
@@ -319,7 +320,7 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
       const int pidx[4] = {yr0 * ncols + xo0[kx], yr0 * ncols + xo1[kx], yr1 * ncols + xo0[kx], yr1 * ncols + xo1[kx]};
 #pragma unroll
       for (int cnr = 0; cnr < 4; ++cnr) {
-        const uint4* p = reinterpret_cast<const uint4*>(tail_smem + (pidx[cnr] * kTailCh + tap * 32) * 2);
+        const uint4* p = reinterpret_cast<const uint4*>(tail_smem + pidx[cnr] * kTailPitch + tap * 64);
         const float wv = wgt[cnr];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

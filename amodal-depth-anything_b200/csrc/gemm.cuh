@@ -318,7 +318,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // ---- stage this N tile's bias / gamma in shared memory: barrier (previous tile's readers done) -> write -> barrier
       float* s_bias = s_vec;
       float* s_gamma = s_bias + 256;
-      if (tma_out) {
+      // (no bias and no gamma: the vectors are tile-invariant -- staged once for the first tile, then no barriers)
+      if (tma_out && (g.bias != nullptr || g.gamma != nullptr || t == unit)) {
         named_bar_sync(1, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;

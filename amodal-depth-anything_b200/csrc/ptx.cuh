@@ -11,6 +11,8 @@ namespace ada {
 // Device-side error mailbox: a kernel that times out on a barrier records why and traps, so a
 // protocol bug surfaces as a CUDA error with a reason instead of hanging the GPU.
 __device__ unsigned int g_dev_error[4];
+// Bring-up timeline buffer (clock64 stamps written by instrumented kernel variants, read through ada_debug_timeline).
+__device__ long long g_dev_timeline[512];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

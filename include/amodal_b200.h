@@ -81,6 +81,8 @@ void ada_destroy(ada_handle h);
 const char* ada_last_error(void);
 /* Device error mailbox written by a kernel that timed out on a barrier (4 words: code, block, parity, thread). */
 int ada_device_error(uint32_t out[4]);
+/* Bring-up hook: clock64 stamps written by instrumented kernel variants (e.g. ADA_ATT_VARIANT=10); n <= 512. */
+int ada_debug_timeline(long long* out, int32_t n);
 
 /* ---- host utility (runs on the CPU; no device needed) -------------------------------------------------------- */
 /* Replaces interpolate_pos_encoding (dinov2.py:199-230): bicubic (A=-0.75, align_corners=False, scale_factor =
