@@ -965,6 +965,7 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
       e.bias = w.bqkv;
       e.out_bf16 = m->qkv;
       e.ldo = 3 * D;
+      e.f16_from_col = 2 * D;  // V is consumed as fp16 by the attention kernel (fp16 probabilities)
       linear(m->xn, M, D, D, w.wqkv, 3 * D, D, e, st);
     }
     launch_attention(m->qkv, m->att, B, N, heads, st);
@@ -1350,6 +1351,7 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     e.ks = d->ks;
     e.cout = d->cout;
     e.sigmoid = d->sigmoid;
+    e.f16_from_col = d->f16_from_col;
     if (d->epi == EPI_CONVT) {
       e.H = d->H;
       e.W = d->W;

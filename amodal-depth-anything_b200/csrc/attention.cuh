@@ -3,7 +3,12 @@
 // without materialising the N x N score matrix.
 //
 // One CTA = 128 queries of one (image, head); Q/K/V are read in place from the [B, N, 3, H, 64] QKV GEMM output
-// through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
+// through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware). Q and K are bf16; V is stored by the
+// QKV GEMM epilogue as fp16 because the probabilities are produced as fp16 pairs: ex2.approx.f16x2 evaluates TWO
+// exponentials per MUFU operation and its result word is the packed P operand as is (no convert, no pack). The kernel
+// was MUFU bound (clock64 timeline: 64 ex2 per thread = 1235 cycles with two warps per scheduler, 1024 of them MUFU
+// pipe); fp16 P (11-bit mantissa) is also more accurate than the bf16 P it replaces. Row sums are accumulated in fp16x2
+// over 4 words and folded into fp32.
 //   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
 //   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)        -> TMEM cols [0,128)
 //                                 O += P V   (128x64x128, P from TMEM, V MN-major smem)  -> TMEM cols [192,256)
@@ -122,7 +127,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+    constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // fp16 P (TMEM) x fp16 V (MN-major: d contiguous)
     auto issue_s = [&](int j) {
       const int s = j & 1;
       mbar_wait(k_full(s), (j >> 1) & 1, 0x520 + s);
@@ -237,39 +242,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         }
       }
       const float mc = m_used * c;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent row-sum chains
       uint32_t pk[32];
+      float lsum = 0.f;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float x0 = fmaf(__uint_as_float(h ? s1[i] : s0[i]), c, -mc);
-          const float x1 = fmaf(__uint_as_float(h ? s1[i + 1] : s0[i + 1]), c, -mc);
-          float p0, p1;
-          if constexpr (VARIANT == 2 || VARIANT == 9) {
-            p0 = x0;
-            p1 = x1;
-          } else if constexpr (VARIANT == 1) {
-            p0 = fast_exp2(x0);
-            p1 = fast_exp2(x1);
-          } else {
-            // The exponentials are MUFU bound (clock64 timeline: 64 ex2 per thread take ~1235 cycles with two warps per
-            // scheduler = 1024 cycles of MUFU pipe). One pair in four goes to the FMA pipe instead; more than that and
-            // the extra ~9 instructions per element make the schedulers issue bound (measured: 3/8 gave no gain).
-            if (((i >> 1) & 3) == 3) {
-              p0 = exp2_fma(x0);
-              p1 = exp2_fma(x1);
+        for (int g8 = 0; g8 < 4; ++g8) {  // 4 score pairs (8 keys): fp16x2 tree sum of the 4 words, then fp32
+          uint32_t hs[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int e = (g8 * 4 + w) * 2;  // element index of the pair inside the chunk
+            const float x0 = fmaf(__uint_as_float(h ? s1[e] : s0[e]), c, -mc);
+            const float x1 = fmaf(__uint_as_float(h ? s1[e + 1] : s0[e + 1]), c, -mc);
+            uint32_t pw;
+            if constexpr (VARIANT == 2 || VARIANT == 9) {
+              pw = pack_f16x2(x0, x1);
             } else {
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
+              pw = ex2_f16x2(pack_f16x2(x0, x1));
             }
+            pk[h * 16 + g8 * 4 + w] = pw;
+            hs[w] = pw;
           }
-          rs[(i >> 1) & 3] += p0;
-          rs[4 + ((i >> 1) & 3)] += p1;
-          pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          lsum += f16x2_sum_f32(add_f16x2(add_f16x2(hs[0], hs[1]), add_f16x2(hs[2], hs[3])));
         }
       }
-      l_part += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      l_part += lsum;
       stamp(j, 4);
       if (j > 0) {  // P(j-1) V(j-1) must have retired before P is overwritten / O may be rescaled
         mbar_wait(o_full, (j - 1) & 1, 0x570);

@@ -70,6 +70,7 @@ struct GemmArgs {
   int ks, cout;             // EPI_CONVT: kernel == stride, output channels
   int sigmoid;              // EPI_TAIL
   int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
+  int f16_from_col;         // EPI_BF16: output columns >= this are stored as fp16 instead of bf16 (V of the QKV GEMM); 0 = off
 };
 
 template <int BN, int CG>
@@ -393,8 +394,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                       if (g.resid2) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid2 + off));
                     }
                   }
+                  if (g.f16_from_col > 0 && oc >= g.f16_from_col) {
 #pragma unroll
-                  for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+                    for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_f16x2(v[j], v[j + 1]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+                  }
                 }
               }
             }
