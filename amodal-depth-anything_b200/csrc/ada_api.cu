@@ -237,6 +237,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   // output maps for the TMA-store epilogues (dummy = tb otherwise; never dereferenced)
   CUtensorMap tc = tb, tc2 = tb;
   g.has_relu_copy = 0;
+  {
+    static const int dbg = env_int("ADA_GEMM_TIMELINE", 0);
+    g.debug_timeline = dbg;
+  }
   if (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU) {
     const int n_out = (g.epi == EPI_SWIGLU) ? L.N / 2 : L.N;
     ADA_REQUIRE(g.out_bf16 != nullptr && g.ldo % 8 == 0 && n_out % 8 == 0, "bf16 output needs ldo, N multiples of 8");
@@ -306,20 +310,18 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
     attr_set = true;
   }
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
-  uint32_t box[3] = {64, 128, 1};
-  CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
+  uint32_t box_q[3] = {64, kAttQ, 1}, box_kv[3] = {64, kAttKV, 1};
+  CUtensorMap tmq = make_tmap_bf16(qkv, 3, dims, str, box_q);
+  CUtensorMap tmkv = make_tmap_bf16(qkv, 3, dims, str, box_kv);
   uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
-  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
+  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box_q);
   AttArgs a;
   a.B = B;
   a.N = N;
@@ -328,13 +330,10 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-  switch (variant) {
-    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 10: attention_tcgen05_kernel<10><<<grid, kAttThreads, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0), st>>>(tm, tmo, a); break;
-    default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-  }
+  if (variant == 2)
+    attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
+  else
+    attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
@@ -965,7 +964,6 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
       e.bias = w.bqkv;
       e.out_bf16 = m->qkv;
       e.ldo = 3 * D;
-      e.f16_from_col = 2 * D;  // V is consumed as fp16 by the attention kernel (fp16 probabilities)
       linear(m->xn, M, D, D, w.wqkv, 3 * D, D, e, st);
     }
     launch_attention(m->qkv, m->att, B, N, heads, st);

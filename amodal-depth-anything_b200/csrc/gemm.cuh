@@ -70,6 +70,7 @@ struct GemmArgs {
   int ks, cout;             // EPI_CONVT: kernel == stride, output channels
   int sigmoid;              // EPI_TAIL
   int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
+  int debug_timeline;       // bring-up: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase into g_dev_timeline
   int f16_from_col;         // EPI_BF16: output columns >= this are stored as fp16 instead of bf16 (V of the QKV GEMM); 0 = off
 };
 
@@ -287,9 +288,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool tma_out = (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU);
+    const bool tl = g.debug_timeline && blockIdx.x == 0 && warp == 4 && lane == 0;
+    int tl_i = 0;
+    auto stamp = [&](int k) {
+      if (tl && tl_i < 60) g_dev_timeline[tl_i * 8 + k] = clock64();
+    };
     for (int t = unit; t < num_tiles; t += num_units) {
       const int mt = t / tiles_n, nt = t % tiles_n;
       const int n0 = nt * BN;
+      stamp(0);
       // ---- map accumulator row -> output row
       bool valid;
       long long orow;  // output row index (pixels / tokens)
@@ -330,8 +337,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         named_bar_sync(1, kEpiThreads);
       }
 
+      stamp(1);
       mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
       tc_fence_after();
+      stamp(2);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
       if (tma_out) {
@@ -405,11 +414,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
             // ---- registers -> swizzled staging buffer -> TMA store
+            stamp(3);
             const int passes = g.has_relu_copy ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
               const uint32_t buf = buf0 + static_cast<uint32_t>(sbuf) * 4096u;
               if (lane == 0) bulk_wait_read<Cfg::kStgBufs - 1>();  // the store that last used this buffer has drained it
               __syncwarp();
+              stamp(4);
               if (pass == 1) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {  // relu on packed bf16 pairs: clear negatives (sign bit set)
@@ -425,6 +436,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                              pk[4 * c + 2], pk[4 * c + 3]);
               fence_proxy_async_smem();
               __syncwarp();
+              stamp(5);
               if (lane == 0) {
                 const CUtensorMap* tm = (pass == 0) ? &tmap_c : &tmap_c2;
                 if (g.a_mode == A_CONV3X3)
@@ -505,6 +517,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       // accumulator stage drained -> hand it back to the MMA warp
+      stamp(6);
+      ++tl_i;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
