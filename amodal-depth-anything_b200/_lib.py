@@ -69,7 +69,6 @@ class GemmDesc(ctypes.Structure):
         ("sigmoid", c_int32),
         ("force_bn", c_int32),
         ("force_cg", c_int32),
-        ("f16_from_col", c_int32),
     ]
 
 

@@ -93,13 +93,13 @@ static int env_int(const char* name, int dflt) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM launcher
-template <int BN, int CG>
+template <int BN, int CG, int EPI>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                            const GemmArgs& g, int num_tiles, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -116,7 +116,7 @@ static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const C
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG > 1) ? 1 : 0;
-  ADA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, ta, tb, tc, tc2, g));
+  ADA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, EPI>, ta, tb, tc, tc2, g));
 }
 
 static int pick_bn(int N) {
@@ -197,7 +197,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     static const int cg_env = env_int("ADA_GEMM_CG", 0);
     const int want = L.force_cg ? L.force_cg : cg_env;
     const int tiles_n_ = (L.N + bn - 1) / bn;
-    bool ok = (bn == 256 || (want == 2 && bn == 128)) && g.epi != EPI_TAIL;  // N=128 pairs are smem-read bound (A 4 KB + B 2 KB / 32 clk)
+    bool ok = (bn == 256 || (want == 2 && bn == 128 && g.epi == EPI_BF16)) && g.epi != EPI_TAIL;  // N=128 pairs are smem-read bound (A 4 KB + B 2 KB / 32 clk)
     if (ok && L.a_mode == A_CONV3X3) {
       const int pad1 = (L.W + kTileW - 1) / kTileW * kTileW, pad2 = (L.W + 2 * kTileW - 1) / (2 * kTileW) * 2 * kTileW;
       const long long pairs = static_cast<long long>(L.batch) * ((L.H + kTileH - 1) / kTileH) * (pad2 / (2 * kTileW)) * tiles_n_;
@@ -273,17 +273,34 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     prof.r->k = static_cast<int>(kreal);
     prof.r->tag = g.epi | (g.act << 4) | (bn << 8) | (cg << 20);
   }
-  if (cg == 2) {
-    if (bn == 128) launch_gemm_bn<128, 2>(ta, tb, tc, tc2, g, num_tiles, st);
-    else launch_gemm_bn<256, 2>(ta, tb, tc, tc2, g, num_tiles, st);
-  } else {
-    switch (bn) {
-      case 32: launch_gemm_bn<32, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
-      case 64: launch_gemm_bn<64, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
-      case 128: launch_gemm_bn<128, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
-      default: launch_gemm_bn<256, 1>(ta, tb, tc, tc2, g, num_tiles, st); break;
-    }
+  // one instantiation per (tile, pairing, epilogue): keeps each kernel's code small (instruction-cache resident)
+#define ADA_GEMM_CASE(BN_, CG_, EPI_)                                      \
+  if (bn == BN_ && cg == CG_ && g.epi == EPI_) {                           \
+    launch_gemm_bn<BN_, CG_, EPI_>(ta, tb, tc, tc2, g, num_tiles, st);     \
+    launched = true;                                                       \
   }
+  bool launched = false;
+  ADA_GEMM_CASE(64, 1, EPI_BF16)
+  ADA_GEMM_CASE(128, 1, EPI_BF16)
+  ADA_GEMM_CASE(128, 2, EPI_BF16)
+  ADA_GEMM_CASE(256, 1, EPI_BF16)
+  ADA_GEMM_CASE(256, 2, EPI_BF16)
+  ADA_GEMM_CASE(128, 1, EPI_SWIGLU)
+  ADA_GEMM_CASE(256, 1, EPI_SWIGLU)
+  ADA_GEMM_CASE(256, 2, EPI_SWIGLU)
+  ADA_GEMM_CASE(64, 1, EPI_EMBED)
+  ADA_GEMM_CASE(128, 1, EPI_EMBED)
+  ADA_GEMM_CASE(256, 1, EPI_EMBED)
+  ADA_GEMM_CASE(256, 2, EPI_EMBED)
+  ADA_GEMM_CASE(64, 1, EPI_CONVT)
+  ADA_GEMM_CASE(128, 1, EPI_CONVT)
+  ADA_GEMM_CASE(256, 1, EPI_CONVT)
+  ADA_GEMM_CASE(256, 2, EPI_CONVT)
+  ADA_GEMM_CASE(32, 1, EPI_TAIL)
+#undef ADA_GEMM_CASE
+  if (!launched)
+    throw AdaError(ADA_EINVAL, "no GEMM instantiation for BN=" + std::to_string(bn) + " CG=" + std::to_string(cg) +
+                                   " epi=" + std::to_string(g.epi));
   ++g_launches;
 }
 
@@ -310,18 +327,20 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
     attr_set = true;
   }
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
-  uint32_t box_q[3] = {64, kAttQ, 1}, box_kv[3] = {64, kAttKV, 1};
-  CUtensorMap tmq = make_tmap_bf16(qkv, 3, dims, str, box_q);
-  CUtensorMap tmkv = make_tmap_bf16(qkv, 3, dims, str, box_kv);
+  uint32_t box[3] = {64, 128, 1};
+  CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
   uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
-  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box_q);
+  CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
   AttArgs a;
   a.B = B;
   a.N = N;
@@ -330,10 +349,13 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-  if (variant == 2)
-    attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
-  else
-    attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tmq, tmkv, tmo, a);
+  switch (variant) {
+    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 10: attention_tcgen05_kernel<10><<<grid, kAttThreads, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0), st>>>(tm, tmo, a); break;
+    default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+  }
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
@@ -1349,7 +1371,6 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     e.ks = d->ks;
     e.cout = d->cout;
     e.sigmoid = d->sigmoid;
-    e.f16_from_col = d->f16_from_col;
     if (d->epi == EPI_CONVT) {
       e.H = d->H;
       e.W = d->W;

@@ -3,31 +3,35 @@
 // without materialising the N x N score matrix.
 //
 // One CTA = 128 queries of one (image, head); Q/K/V are read in place from the [B, N, 3, H, 64] QKV GEMM output
-// through 3-D TMA maps (out-of-range tokens are zero-filled by the hardware). KV tiles are 64 keys wide so that BOTH the
-// score tile and the probability tile can be double-buffered inside 256 TMEM columns (two CTAs per SM):
-//     S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
-//   warp 0     : TMA producer (Q once, then 4-stage K and V rings of 8 KB tiles)
-//   warp 1     : tcgen05 issuer.  S_b = Q K_j^T (128x64x64, K-major operands)      for tile j+2 while softmax works on j
-//                                 O  += P_b V_j  (128x64x64, P from TMEM, V MN-major from smem)
-//   warps 2..5 : softmax. Each thread owns one query row (= one TMEM lane): it pulls its 64 scores into registers
-//                (tcgen05.ld), releases the S buffer, exponentiates against a *stale* row maximum, writes bf16 P back to
-//                TMEM (tcgen05.st) and signals the issuer. Row max / row sum need no shuffles.
-// Softmax -> issuer hand-offs are hardware named barriers (bar.arrive / bar.sync), issuer -> softmax are mbarriers
-// (tcgen05.commit). Why this shape: measured on the 128-key single-buffered version, the barrier round trip softmax -> issuer -> tensor
-// pipe -> softmax alone (no math at all) cost 0.233 ms of the 0.39 ms kernel; with S and P double-buffered the softmax
-// warps never wait on it. The accumulator stays in TMEM and is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when a
-// row maximum grows by more than 2^8 (first tile or two); p may reach 256, harmless in fp32/bf16, and O / l is exact.
-// The kernel is MUFU (ex2) / issue bound at head_dim 64: 128 x 128 exponentials per 128 keys = 1024 cycles per SM.
+// through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
+//   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
+//   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)        -> TMEM cols [0,128)
+//                                 O += P V   (128x64x128, P from TMEM, V MN-major smem)  -> TMEM cols [192,256)
+//   warps 2..9 : softmax, EIGHT warps: every query row (= TMEM lane) is shared by two threads that each own 64 of the
+//                128 score columns (warps w and w+4 sit on the same TMEM lane quarter). The pair exchanges its partial
+//                row maximum through shared memory; everything else is thread-private. ncu on the 4-warp version showed
+//                the softmax warps busy 83% of the time at 0.25 IPC each (fixed-latency dependency stalls) with the
+//                tensor pipe at 30% and MUFU at 61%: the kernel needed more warps per scheduler, not fewer instructions.
+//                P is written back to TMEM (cols [128,192), bf16 pairs) with tcgen05.st and consumed by the P V MMA
+//                straight from there; S is released to the issuer as soon as it sits in registers.
+// The running output stays in TMEM across KV tiles. Rows are kept relative to a *stale* maximum: the accumulator is only
+// rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row's maximum grows by more than 2^8, which happens in the first
+// tile or two; p may then reach 256, harmless in fp32/bf16, and O / l is exact either way.
+// Two CTAs fit per SM (80 KB smem, 256 TMEM columns, 96 registers x 320 threads each).
+// Variants tried and measured on the same shape (B=32, N=1370, 16 heads; numbers in profiles/README.md): 64-key tiles
+// with S and P double-buffered (0.42 ms), two query tiles per CTA sharing K/V (0.49 ms), fp16-pair exponentials
+// (ex2.approx.f16x2 is issued as two MUFU.EX2.F16, no gain), against 0.38 ms for this kernel; MUFU sits at 61 % with the
+// two resident CTAs' non-exponential phases (row max + pair exchange, TMEM ld/st, waits: ~830 of ~2800 cycles per tile)
+// only partly overlapped.
 #pragma once
 #include "ptx.cuh"
 
 namespace ada {
 
-constexpr int kAttThreads = 192;
-constexpr int kAttQ = 128, kAttKV = 64, kAttD = 64;
-constexpr int kAttStages = 4;
-constexpr int kAttTileBytes = kAttKV * kAttD * 2;  // 8 KB
-constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * kAttStages * kAttTileBytes /*K,V*/ + 256 /*barriers*/;
+constexpr int kAttThreads = 320;
+constexpr int kAttSoftmaxThreads = 256;
+constexpr int kAttQ = 128, kAttKV = 128, kAttD = 64;
+constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 3072 /*pair exchange*/ + 256 /*barriers*/;
 constexpr int kAttTmemCols = 256;
 constexpr float kAttRescaleLog2 = 8.0f;  // rescale O only when a row max grows by more than 2^8
 
@@ -36,26 +40,23 @@ struct AttArgs {
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
-// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 2 = exponentials replaced by a copy (timing skeleton
-// only, wrong results).
+// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = every exponential on MUFU, 2 = exponentials
+// replaced by a copy (timing skeleton only, wrong results), 9 = 2 + no K/V reloads, 10 = clock64 timeline of one thread.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         const __grid_constant__ CUtensorMap tmap_out, const AttArgs a) {
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+                         const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
-  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sK + kAttStages * kAttTileBytes;
-  const uint32_t bar = sV + kAttStages * kAttTileBytes;
-  const uint32_t q_full = bar;
-  auto s_full = [&](int b) { return bar + 8 + 8u * b; };
-  auto s_free = [&](int b) { return bar + 24 + 8u * b; };
-  auto p_full = [&](int b) { return bar + 40 + 8u * b; };
-  auto pv_done = [&](int b) { return bar + 56 + 8u * b; };
-  auto k_full = [&](int s) { return bar + 72 + 8u * s; };
-  auto k_empty = [&](int s) { return bar + 104 + 8u * s; };
-  auto v_full = [&](int s) { return bar + 136 + 8u * s; };
-  auto v_empty = [&](int s) { return bar + 168 + 8u * s; };
-  const uint32_t tmem_ptr_smem = bar + 200;
+  const uint32_t sQ = sbase, sK = sbase + 16384, sV = sbase + 49152;
+  float* xch = reinterpret_cast<float*>(att_smem + 81920);  // [3][2][128]: row-max exchange (2 parities) + row sums
+  const uint32_t bar = sbase + 81920 + 3072;
+  const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24, s_free = bar + 32;
+  auto k_full = [&](int s) { return bar + 40 + 8u * s; };
+  auto k_empty = [&](int s) { return bar + 56 + 8u * s; };
+  auto v_full = [&](int s) { return bar + 72 + 8u * s; };
+  auto v_empty = [&](int s) { return bar + 88 + 8u * s; };
+  const uint32_t tmem_ptr_smem = bar + 104;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAttQ, head = blockIdx.y, img = blockIdx.z;
@@ -66,16 +67,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       g_dev_error[0] = 0xA11;
       __trap();
     }
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_qkv);
     mbar_init(q_full, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1);
-      mbar_init(s_free(b), 128);
-      mbar_init(p_full(b), 128);
-      mbar_init(pv_done(b), 1);
-    }
-    for (int s = 0; s < kAttStages; ++s) {
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kAttSoftmaxThreads);
+    mbar_init(o_full, 1);
+    mbar_init(s_free, kAttSoftmaxThreads);
+    for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1);
@@ -98,95 +96,109 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &tmap_q, q_full, head * kAttD, q0, img);
+      tma_load_3d(sQ, &tmap_qkv, q_full, head * kAttD, q0, img);
     }
     for (int j = 0; j < num_kv; ++j) {
-      const int s = j % kAttStages;
-      const uint32_t ph = (j / kAttStages) & 1;
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
       mbar_wait(k_empty(s), ph ^ 1u, 0x500 + s);
       if (lane == 0) {
-        mbar_expect_tx(k_full(s), kAttTileBytes);
-        tma_load_3d(sK + s * kAttTileBytes, &tmap_kv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
+        if (VARIANT == 9 && j >= 2) {
+          mbar_arrive(k_full(s));  // measurement: reuse the resident tile, no L2 -> SM traffic
+        } else {
+          mbar_expect_tx(k_full(s), 16384);
+          tma_load_3d(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
+        }
       }
       mbar_wait(v_empty(s), ph ^ 1u, 0x510 + s);
       if (lane == 0) {
-        mbar_expect_tx(v_full(s), kAttTileBytes);
-        tma_load_3d(sV + s * kAttTileBytes, &tmap_kv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
+        if (VARIANT == 9 && j >= 2) {
+          mbar_arrive(v_full(s));
+        } else {
+          mbar_expect_tx(v_full(s), 16384);
+          tma_load_3d(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
+        }
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, kAttKV, 0, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, kAttD, 0, 1);  // B = V is MN-major (d contiguous)
-    auto issue_s = [&](int j) {  // S_{j&1} = Q K_j^T
-      const int s = j % kAttStages;
-      mbar_wait(k_full(s), (j / kAttStages) & 1, 0x520 + s);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+    auto issue_s = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(k_full(s), (j >> 1) & 1, 0x520 + s);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t da = make_smem_desc_sw128(sQ + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sK + s * kAttTileBytes + k * 32, 16, 1024);
-          umma_bf16_ss(tS + (j & 1) * 64, da, db, idesc_s, k > 0 ? 1u : 0u);
+          const uint64_t db = make_smem_desc_sw128(sK + s * 16384 + k * 32, 16, 1024);
+          umma_bf16_ss(tS, da, db, idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(k_empty(s));
-        umma_commit(s_full(j & 1));
+        umma_commit(s_full);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0, 0x530);
     issue_s(0);
-    if (num_kv > 1) issue_s(1);
     for (int j = 0; j < num_kv; ++j) {
-      const int b = j & 1, s = j % kAttStages;
-      const uint32_t ph = (j >> 1) & 1;
-      named_bar_sync(8 + b, 160);  // P_b(j) in TMEM (and S_b(j) consumed, O rescaled if it had to be)
-      mbar_wait(v_full(s), (j / kAttStages) & 1, 0x550 + s);
+      const int s = j & 1;
+      if (j + 1 < num_kv) {
+        named_bar_sync(6, kAttSoftmaxThreads + 32);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
+        issue_s(j + 1);
+      }
+      named_bar_sync(7, kAttSoftmaxThreads + 32);  // P(j) in TMEM, O rescaled if needed
+      mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
-          const uint64_t db = make_smem_desc_sw128(sV + s * kAttTileBytes + kk * 2048, 0, 1024);
-          umma_bf16_ts(tO, tP + b * 32 + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
+          const uint64_t db = make_smem_desc_sw128(sV + s * 16384 + kk * 2048, 0, 1024);
+          umma_bf16_ts(tO, tP + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(v_empty(s));
-        umma_commit(pv_done(b));
+        umma_commit(o_full);
       }
       __syncwarp();
-      if (j + 2 < num_kv) {
-        named_bar_sync(6 + b, 160);  // arrived long ago (S_b(j) was pulled into registers before P_b(j) was written)
-        issue_s(j + 2);
-      }
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
-    const int qd = warp & 3;
+    const int qd = warp & 3;               // TMEM lane quarter
+    const int half = (warp - 2) >> 2;      // which 64 score columns of the row this thread owns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float c = a.scale_log2e;
-    float m_used = -INFINITY, l_run = 0.f;
+    float m_used = -INFINITY, l_part = 0.f;
 
+    const bool tl = (VARIANT == 10) && threadIdx.x == 64 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
+    auto stamp = [&](int j, int k) {
+      if (tl) g_dev_timeline[j * 8 + k] = clock64();
+    };
     for (int j = 0; j < num_kv; ++j) {
-      const int b = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const int kv_valid = min(kAttKV, a.N - j * kAttKV);
-      mbar_wait(s_full(b), ph, 0x560 + b);
+      const int kv_valid = min(kAttKV, a.N - j * kAttKV) - half * 64;  // valid keys inside this thread's 64 columns
+      stamp(j, 0);
+      mbar_wait(s_full, j & 1, 0x560);
+      stamp(j, 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
-      tmem_ld32(tS + lane_off + b * 64, s0);
-      tmem_ld32(tS + lane_off + b * 64 + 32, s1);
+      tmem_ld32(tS + lane_off + half * 64, s0);
+      tmem_ld32(tS + lane_off + half * 64 + 32, s1);
       tmem_ld_wait();
+      stamp(j, 2);
       tc_fence_before();
-      if (j + 2 < num_kv) named_bar_arrive(6 + b, 160);  // S_b(j) now lives in registers -> S(j+2) may overwrite it
-      if (kv_valid < kAttKV) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
+      // this thread's part of S(j) now lives in registers. Hardware named barriers (arrive here, sync in the issuer warp)
+      // hand off in tens of cycles; the mbarrier round trip they replace cost ~350 cycles per hop and made the kernel
+      // synchronisation-latency bound (skeleton 0.23 ms of 0.39 ms with all math removed).
+      if (j + 1 < num_kv) named_bar_arrive(6, kAttSoftmaxThreads + 32);
+      if (kv_valid < 64) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= kv_valid) s0[i] = 0xff800000u;
           if (32 + i >= kv_valid) s1[i] = 0xff800000u;
         }
       }
-      // 8 independent max chains
       float tm[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -203,34 +215,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) tm[i] = fmaxf(tm[i], tm[i + 4]);
-      const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
+      float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
+      // ---- the two owners of a row combine their partial maxima (double-buffered by tile parity)
+      float* xm = xch + (j & 1) * 256;
+      xm[half * 128 + row] = tmax;
+      named_bar_sync(1 + qd, 64);
+      tmax = fmaxf(tmax, xm[(half ^ 1) * 128 + row]);
+      stamp(j, 3);
 
-      // ---- running (stale) maximum
+      // ---- running (stale) maximum: both owners take the same decision from the same combined maximum
+      float sc = 1.0f;
+      bool rescale = false;
       if (j == 0) {
         m_used = tmax;
       } else {
         const bool grow = (tmax - m_used) * c > kAttRescaleLog2;
-        if (__any_sync(0xffffffffu, grow)) {  // rare: bring this warp's 32 accumulator rows to the new maxima
+        rescale = __any_sync(0xffffffffu, grow);  // rare (first tile or two); identical in both warps of the pair
+        if (rescale) {
           const float m_new = fmaxf(m_used, tmax);
-          const float sc = fast_exp2((m_used - m_new) * c);
+          sc = fast_exp2((m_used - m_new) * c);
           m_used = m_new;
-          l_run *= sc;
-          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1, 0x570);  // every P V issued so far has retired
-          tc_fence_after();
-#pragma unroll 1
-          for (int h = 0; h < 8; ++h) {  // 8 columns at a time: keep the register footprint of this path small
-            uint32_t r[8];
-            tmem_ld8(tO + lane_off + h * 8, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
-            tmem_st8(tO + lane_off + h * 8, r);
-          }
-          tmem_st_wait();
+          l_part *= sc;
         }
       }
       const float mc = m_used * c;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent row-sum chains
       uint32_t pk[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -239,43 +248,70 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           const float x0 = fmaf(__uint_as_float(h ? s1[i] : s0[i]), c, -mc);
           const float x1 = fmaf(__uint_as_float(h ? s1[i + 1] : s0[i + 1]), c, -mc);
           float p0, p1;
-          if constexpr (VARIANT == 2) {
+          if constexpr (VARIANT == 2 || VARIANT == 9) {
             p0 = x0;
             p1 = x1;
-          } else {
+          } else if constexpr (VARIANT == 1) {
             p0 = fast_exp2(x0);
             p1 = fast_exp2(x1);
+          } else {
+            // The exponentials are MUFU bound (clock64 timeline: 64 ex2 per thread take ~1235 cycles with two warps per
+            // scheduler = 1024 cycles of MUFU pipe). One pair in four goes to the FMA pipe instead; more than that and
+            // the extra ~9 instructions per element make the schedulers issue bound (measured: 3/8 gave no gain).
+            if (((i >> 1) & 3) == 3) {
+              p0 = exp2_fma(x0);
+              p1 = exp2_fma(x1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
           }
           rs[(i >> 1) & 3] += p0;
           rs[4 + ((i >> 1) & 3)] += p1;
           pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
         }
       }
-      l_run += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
-      if (j >= 2) {  // P_b was last read by P V (j-2)
-        mbar_wait(pv_done(b), ((j - 2) >> 1) & 1, 0x575 + b);
+      l_part += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      stamp(j, 4);
+      if (j > 0) {  // P(j-1) V(j-1) must have retired before P is overwritten / O may be rescaled
+        mbar_wait(o_full, (j - 1) & 1, 0x570);
         tc_fence_after();
+        if (rescale) {  // bring this warp's share (32 of the 64 columns) of its 32 accumulator rows to the new maxima
+#pragma unroll 1
+          for (int h = 0; h < 4; ++h) {
+            uint32_t r[8];
+            tmem_ld8(tO + lane_off + half * 32 + h * 8, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
+            tmem_st8(tO + lane_off + half * 32 + h * 8, r);
+          }
+        }
       }
-      tmem_st32(tP + lane_off + b * 32, pk);
+      stamp(j, 5);
+      tmem_st32(tP + lane_off + half * 32, pk);
       tmem_st_wait();
+      stamp(j, 6);
       tc_fence_before();
-      named_bar_arrive(8 + b, 160);
+      named_bar_arrive(7, kAttSoftmaxThreads + 32);
     }
     // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile is dead once the last S MMA has retired) -> one TMA
     //      store per CTA (row-per-thread global stores touch 32 cache lines per warp instruction).
-    mbar_wait(pv_done((num_kv - 1) & 1), ((num_kv - 1) >> 1) & 1, 0x580);
+    float* xl = xch + 512;
+    xl[half * 128 + row] = l_part;
+    mbar_wait(o_full, (num_kv - 1) & 1, 0x580);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
+    named_bar_sync(1 + qd, 64);
+    const float inv = 1.0f / (l_part + xl[(half ^ 1) * 128 + row]);
     const uint32_t o_row = sQ + static_cast<uint32_t>(row) * 128u;
     const uint32_t o_sw = static_cast<uint32_t>(row & 7);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    {
       uint32_t r[32];
-      tmem_ld32(tO + lane_off + h * 32, r);
+      tmem_ld32(tO + lane_off + half * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t chunk = static_cast<uint32_t>(h * 4 + i);
+        const uint32_t chunk = static_cast<uint32_t>(half * 4 + i);
         st_shared_v4(o_row + ((chunk ^ o_sw) << 4),
                      pack_bf16x2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
                      pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
@@ -284,7 +320,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(5, kAttSoftmaxThreads);
     if (threadIdx.x == 64) {  // first softmax thread; rows past N are clipped by the tensor map
       tma_store_3d(&tmap_out, sQ, head * kAttD, q0, img);
       bulk_commit();

@@ -71,7 +71,6 @@ struct GemmArgs {
   int sigmoid;              // EPI_TAIL
   int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
   int debug_timeline;       // bring-up: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase into g_dev_timeline
-  int f16_from_col;         // EPI_BF16: output columns >= this are stored as fp16 instead of bf16 (V of the QKV GEMM); 0 = off
 };
 
 template <int BN, int CG>
@@ -115,7 +114,9 @@ __device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4 rr) {
   v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
 }
 
-template <int BN, int CG>
+// EPI is a compile-time parameter: with every epilogue inlined behind run-time switches the kernel was ~4500 SASS
+// instructions and ncu showed the epilogue warps stalled on instruction fetch (stall_no_inst) on every tile.
+template <int BN, int CG, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
@@ -287,7 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t st_sw = static_cast<uint32_t>(lane & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool tma_out = (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU);
+    constexpr bool tma_out = (EPI == EPI_BF16 || EPI == EPI_SWIGLU);
     const bool tl = g.debug_timeline && blockIdx.x == 0 && warp == 4 && lane == 0;
     int tl_i = 0;
     auto stamp = [&](int k) {
@@ -318,7 +319,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         valid = m < g.M;
         orow = m;
       }
-      if (g.epi == EPI_EMBED) {
+      if constexpr (EPI == EPI_EMBED) {
         const int b = m / g.P, p = m % g.P;
         orow = static_cast<long long>(b) * (g.P + 1) + 1 + p;
       }
@@ -327,7 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float* s_bias = s_vec;
       float* s_gamma = s_bias + 256;
       // (no bias and no gamma: the vectors are tile-invariant -- staged once for the first tile, then no barriers)
-      if (tma_out && (g.bias != nullptr || g.gamma != nullptr || t == unit)) {
+      if (tma_out && (g.bias != nullptr || g.gamma != nullptr || t == unit)) {  // tma_out is constexpr
         named_bar_sync(1, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;
@@ -343,17 +344,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       stamp(2);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      if (tma_out) {
+      if constexpr (tma_out) {
         if constexpr (BN >= 64) {
-          const int out_cols = (g.epi == EPI_SWIGLU) ? BN / 2 : BN;  // output columns produced by this tile
-          const int on0 = (g.epi == EPI_SWIGLU) ? (n0 >> 1) : n0;
-          const int n_out = (g.epi == EPI_SWIGLU) ? (g.N >> 1) : g.N;
+          constexpr int out_cols = (EPI == EPI_SWIGLU) ? BN / 2 : BN;  // output columns produced by this tile
+          const int on0 = (EPI == EPI_SWIGLU) ? (n0 >> 1) : n0;
+          const int n_out = (EPI == EPI_SWIGLU) ? (g.N >> 1) : g.N;
 #pragma unroll 1
           for (int cg = half; cg < out_cols / 64; cg += 2) {
             const int oc = on0 + cg * 64;  // first output column of this 64-wide group
             if (oc >= n_out) break;
             uint32_t pk[32];               // 64 bf16 outputs of this thread's row
-            if (g.epi == EPI_SWIGLU) {
+            if constexpr (EPI == EPI_SWIGLU) {
               // 128 interleaved accumulator columns: [x1 32 | x2 32 | x1 32 | x2 32]
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -403,13 +404,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                       if (g.resid2) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid2 + off));
                     }
                   }
-                  if (g.f16_from_col > 0 && oc >= g.f16_from_col) {
 #pragma unroll
-                    for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_f16x2(v[j], v[j + 1]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
-                  }
+                  for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
                 }
               }
             }
@@ -449,7 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
         }
-      } else if (g.epi == EPI_TAIL) {
+      } else if constexpr (EPI == EPI_TAIL) {
         if constexpr (BN == 32) if (half == 0) {
           uint32_t r[32];
           tmem_ld32(t_addr, r);
@@ -473,7 +469,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           const int nb = n0 + c * 32;
           if (!valid || nb >= g.N) continue;
-          if (g.epi == EPI_EMBED) {
+          if constexpr (EPI == EPI_EMBED) {
             const int p = m % g.P;
             const float* ax = g.aux + static_cast<long long>(p) * g.N + nb;
             float* dst = g.out_f32 + orow * g.ldo + nb;

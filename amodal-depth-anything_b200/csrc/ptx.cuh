@@ -208,12 +208,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 // Instruction descriptor: D=f32, A=B=bf16; majors: 0 = K-major, 1 = MN-major.
-// Same with fp16 operands (format code 0).
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
-}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
@@ -311,26 +305,6 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// two exponentials per MUFU op: 2^x for an fp16 pair (the softmax exponentials are MUFU bound at head_dim 64)
-__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t add_f16x2(uint32_t a, uint32_t b) {
-  uint32_t y;
-  asm("add.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-  return y;
-}
-__device__ __forceinline__ float f16x2_sum_f32(uint32_t v) {
-  const __half2 h = *reinterpret_cast<const __half2*>(&v);
-  const float2 f = __half22float2(h);
-  return f.x + f.y;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

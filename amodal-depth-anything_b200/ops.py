@@ -19,7 +19,7 @@ def _stream():
 
 def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,
          out_relu=None, resid1=None, resid2=None, aux=None, ldo=0, P=0, ks=0, cout=0, sigmoid=0, force_bn=0,
-         force_cg=0, f16_from_col=0, conv=None, N=None, K=None, M=None, H=0, W=0):
+         force_cg=0, conv=None, N=None, K=None, M=None, H=0, W=0):
     """A: bf16 [M,K] (linear) or NHWC bf16 [B,H,W,Cin] (conv=(B,H,W,Cin)); Wt: bf16 [N,Kw]."""
     lib = L.load()
     d = L.GemmDesc()
@@ -42,7 +42,6 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
         setattr(d, name, t.data_ptr() if t is not None else None)
     d.ldo, d.P, d.ks, d.cout, d.sigmoid, d.force_bn = ldo, P, ks, cout, sigmoid, force_bn
     d.force_cg = force_cg
-    d.f16_from_col = f16_from_col
     L.check(lib.ada_op_gemm(ctypes.byref(d), _stream()))
 
 
