@@ -144,6 +144,19 @@ def test_forward_matches_oracle_vitl_518():
     assert rel <= REL_TOL and absrel <= ABSREL_TOL
 
 
+def test_forward_matches_oracle_vits_1036():
+    """BASELINE config #4 resolution (1036x1036: 5477 tokens, bicubic pos-embed with the 0.1 offset, 74x74 patch grid,
+    long-sequence attention, 592/1036 head maps) on the small encoder so the CPU oracle stays within seconds."""
+    enc, gt = "vits", "mask+observation"
+    sd = synth.make_state_dict(enc, gt, 17)
+    inp = synth.make_inputs(1, 1036, 1036, 17)
+    ref = O.forward(sd, enc, gt, inp["x"], None, inp["guide_mask"], inp["observation"])
+    out = _run(_model(enc, gt, "invisible_part", sd), inp)
+    rel, absrel = _errors(out, ref, inp["mask01"])
+    print(f"vits 1036 rel {rel:.3e} absrel {absrel:.3e}")
+    assert rel <= REL_TOL and absrel <= ABSREL_TOL
+
+
 def test_batch_sharding_is_bit_exact_and_deterministic():
     """Images are independent end to end (no BatchNorm, per-token LN, per-image attention), so running a batch in
     shards -- what the multi-GPU path does -- must reproduce the full-batch result bit for bit."""
