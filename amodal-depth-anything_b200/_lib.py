@@ -34,6 +34,8 @@ class AdaConfig(ctypes.Structure):
         ("sigmoid", c_int32),
         ("pos_grid", c_int32),
         ("interpolate_offset", c_float),
+        ("input_projection", c_int32),
+        ("normalize_input", c_int32),
     ]
 
 

@@ -326,10 +326,16 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   static int variant = 0;
   if (!attr_set) {
     variant = env_int("ADA_ATT_VARIANT", 0);
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+#define ADA_ATT_ATTR(V) \
+  ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes))
+    ADA_ATT_ATTR(0);
+    ADA_ATT_ATTR(1);
+    ADA_ATT_ATTR(2);
+    ADA_ATT_ATTR(3);
+    ADA_ATT_ATTR(4);
+    ADA_ATT_ATTR(5);
+    ADA_ATT_ATTR(9);
+#undef ADA_ATT_ATTR
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
     attr_set = true;
   }
@@ -352,6 +358,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   switch (variant) {
     case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 3: attention_tcgen05_kernel<3><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 4: attention_tcgen05_kernel<4><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 5: attention_tcgen05_kernel<5><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
     case 10: attention_tcgen05_kernel<10><<<grid, kAttThreads, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0), st>>>(tm, tmo, a); break;
     default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
@@ -406,7 +415,7 @@ static void launch_tail_gather(const __nv_bfloat16* V, const float* bias2, const
 }
 
 static void launch_patch_gather(const float* rgb, const float* const* guides, const int* guide_ch, int n_guides,
-                                __nv_bfloat16* out, int B, int H, int W, int Kpad, cudaStream_t st) {
+                                __nv_bfloat16* out, int B, int H, int W, int Kpad, int normalize, cudaStream_t st) {
   ADA_REQUIRE(n_guides >= 0 && n_guides <= 3, "at most 3 guide tensors");
   PatchSrc src{};
   src.ptr[0] = rgb;
@@ -421,8 +430,12 @@ static void launch_patch_gather(const float* rgb, const float* const* guides, co
   ADA_REQUIRE(C * 196 <= Kpad, "patch gather: Kpad too small");
   const long long total = static_cast<long long>(B) * (H / 14) * C * 14 * (W / 14);
   ProfScope prof(PC_GATHER, 0.0, 6.0 * B * C * static_cast<double>(H) * W, st);
-  patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      src, out, B, C, H, W, Kpad, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+  if (normalize)
+    patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        src, out, B, C, H, W, Kpad, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+  else  // un-guided model: the caller normalised the image (infer.py:18)
+    patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, out, B, C, H, W, Kpad, 0.f, 0.f,
+                                                                                     0.f, 1.f, 1.f, 1.f);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
@@ -741,9 +754,11 @@ static void finalize_model(ada_model* m) {
       m->w_rs[i] = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
       m->b_rs[i] = up_f32(m, hd + "resize_layers.3.bias", {Ci});
     }
-    m->ip[i] = up_conv3x3(m, hd + "input_projection." + si + ".0", Ci, Ci, true);
-    m->ipln_w[i] = up_f32(m, hd + "input_projection." + si + ".1.weight", {Ci});
-    m->ipln_b[i] = up_f32(m, hd + "input_projection." + si + ".1.bias", {Ci});
+    if (c.input_projection) {
+      m->ip[i] = up_conv3x3(m, hd + "input_projection." + si + ".0", Ci, Ci, true);
+      m->ipln_w[i] = up_f32(m, hd + "input_projection." + si + ".1.weight", {Ci});
+      m->ipln_b[i] = up_f32(m, hd + "input_projection." + si + ".1.bias", {Ci});
+    }
     m->rn[i] = up_conv3x3(m, hd + "scratch.layer" + std::to_string(i + 1) + "_rn", F, Ci, false);
   }
   for (int k = 1; k <= 4; ++k) {
@@ -847,7 +862,7 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
     maxpix = std::max(maxpix, pix);
     m->proj[i] = b.take<__nv_bfloat16>(BP * Ci);
     m->rs[i] = (i == 2) ? m->proj[i] : b.take<__nv_bfloat16>(pix * Ci);
-    m->ipb[i] = b.take<__nv_bfloat16>(pix * Ci);
+    m->ipb[i] = c.input_projection ? b.take<__nv_bfloat16>(pix * Ci) : m->rs[i];  // un-guided head: layer_i = resize output
     m->rnb[i] = b.take<__nv_bfloat16>(pix * F);
     m->rnr[i] = b.take<__nv_bfloat16>(pix * F);
     reg("layer" + std::to_string(i + 1) + "_rn", m->rnb[i], pix * F, 0);
@@ -956,7 +971,7 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
   } prof_guard(m->profile ? &m->prof : nullptr);
 
   // ---- tokens: patch gather -> embed GEMM (+bias +pos) ; cls rows     (dav2.py:65-76, dinov2.py:232-246)
-  launch_patch_gather(rgb, guides, guide_ch, n_guides, m->a_embed, B, H, W, m->kpad, st);
+  launch_patch_gather(rgb, guides, guide_ch, n_guides, m->a_embed, B, H, W, m->kpad, c.normalize_input, st);
   cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(pc.cls_pos, m->x, B, N, D);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -1065,10 +1080,11 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
       e.ldo = Ci;
       linear(m->col4, B * sh[3] * sw[3], 9 * Ci, 9 * Ci, m->w_rs[3], Ci, 9 * Ci, e, st);
     }
-    // input_projection[i]: conv3x3 + channel LN + ReLU (dpt.py:153-159,178-179)
-    conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
-    launch_channel_ln_relu(m->ipb[i], m->ipln_w[i], m->ipln_b[i], m->ipb[i], static_cast<long long>(B) * sh[i] * sw[i],
-                           Ci, 1e-6f, st);
+    if (c.input_projection) {  // input_projection[i]: conv3x3 + channel LN + ReLU (dpt.py:153-159,178-179)
+      conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
+      launch_channel_ln_relu(m->ipb[i], m->ipln_w[i], m->ipln_b[i], m->ipb[i], static_cast<long long>(B) * sh[i] * sw[i],
+                             Ci, 1e-6f, st);
+    }
     // layer{i}_rn: conv3x3 C_i -> F, no bias (blocks.py:20-24); keep x and relu(x) for the residual units
     conv3x3(m->ipb[i], B, sh[i], sw[i], m->rn[i], ACT_NONE, nullptr, nullptr, m->rnb[i], m->rnr[i], st);
   }
@@ -1185,6 +1201,8 @@ int ada_create(const ada_config* cfg, ada_handle* out) {
     ADA_REQUIRE(cfg->embed_dim % 128 == 0, "embed_dim % 128");
     ADA_REQUIRE(cfg->features % 16 == 0 && cfg->features >= 64, "features must be a multiple of 16, >= 64");
     ADA_REQUIRE(cfg->guide_channels >= 0 && cfg->guide_channels <= 5, "guide_channels in [0,5]");
+    ADA_REQUIRE(cfg->sigmoid >= 0 && cfg->sigmoid <= 2, "sigmoid (final activation) in {0: none, 1: sigmoid, 2: relu}");
+    ADA_REQUIRE((cfg->input_projection | 1) == 1 && (cfg->normalize_input | 1) == 1, "input_projection / normalize_input are flags");
     for (int i = 0; i < 4; ++i) ADA_REQUIRE(cfg->out_channels[i] % 8 == 0, "out_channels % 8");
     ada_model* m = new ada_model();
     m->cfg = *cfg;
@@ -1240,7 +1258,7 @@ int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W) {
   const ada_config& c = h->cfg;
   // gather + cls + embed | per block: 2 LN + 4 GEMM + attention | 4 tap LN | head
   int n = 3 + c.depth * 7 + 4;
-  n += 4 /*projects*/ + 2 /*convT*/ + 2 /*im2col+gemm*/ + 4 * 3 /*ip conv, LN, rn*/;
+  n += 4 /*projects*/ + 2 /*convT*/ + 2 /*im2col+gemm*/ + 4 * (c.input_projection ? 3 : 1) /*ip conv, LN, rn*/;
   n += 3 * 6 + 4 /*refinenets: (2+2+1+1) x3, (2+1+1) for #4*/;
   n += 3 /*oc1, upsample, tail*/;
   if (h->capture) n += 0;
@@ -1418,7 +1436,7 @@ int ada_op_patch_gather(const float* rgb, const float* const* guides, const int3
                         void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t Kpad, void* stream) {
   return guarded([&] {
     require_device();
-    launch_patch_gather(rgb, guides, guide_ch, n_guides, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, Kpad,
+    launch_patch_gather(rgb, guides, guide_ch, n_guides, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, Kpad, 1,
                         static_cast<cudaStream_t>(stream));
   });
 }

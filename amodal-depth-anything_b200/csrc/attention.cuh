@@ -141,15 +141,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       }
       __syncwarp();
     };
+    const bool tli = (VARIANT == 10) && lane == 0 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
+    auto istamp = [&](int j, int k) {
+      if (tli) g_dev_timeline[128 + j * 8 + k] = clock64();
+    };
     mbar_wait(q_full, 0, 0x530);
     issue_s(0);
     for (int j = 0; j < num_kv; ++j) {
       const int s = j & 1;
+      istamp(j, 0);
       if (j + 1 < num_kv) {
         named_bar_sync(6, kAttSoftmaxThreads + 32);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
+        istamp(j, 1);
         issue_s(j + 1);
       }
+      istamp(j, 2);
       named_bar_sync(7, kAttSoftmaxThreads + 32);  // P(j) in TMEM, O rescaled if needed
+      istamp(j, 3);
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
       if (lane == 0) {
@@ -162,6 +170,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         umma_commit(o_full);
       }
       __syncwarp();
+      istamp(j, 4);
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
@@ -199,22 +208,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           if (32 + i >= kv_valid) s1[i] = 0xff800000u;
         }
       }
-      float tm[8];
+      float tm[4];  // FMNMX3: two scores per instruction, four independent chains of 16 scores
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        tm[i] = fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 4]));
-        tm[4 + i] = fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 4]));
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t* v = (k < 2) ? (s0 + 16 * k) : (s1 + 16 * (k - 2));
+        float t = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+#pragma unroll
+        for (int i = 3; i < 15; i += 2) t = fmax3(t, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        tm[k] = fmaxf(t, __uint_as_float(v[15]));
       }
-#pragma unroll
-      for (int i = 8; i < 32; i += 4) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          tm[k] = fmaxf(tm[k], __uint_as_float(s0[i + k]));
-          tm[4 + k] = fmaxf(tm[4 + k], __uint_as_float(s1[i + k]));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tm[i] = fmaxf(tm[i], tm[i + 4]);
       float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
       // ---- the two owners of a row combine their partial maxima (double-buffered by tile parity)
       float* xm = xch + (j & 1) * 256;
@@ -239,39 +241,45 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         }
       }
       const float mc = m_used * c;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent row-sum chains
+      // Scale-and-shift and the row sums run as packed pairs (FFMA2 / FADD2: 182 M instead of 267 M warp instructions per
+      // launch at B=32); kEmuMask picks the pairs (of the 16 in a 32-column half) whose exponential is evaluated on the
+      // FMA pipe instead of MUFU. Measured (B=32, N=1370): none 0.379 ms, 4/16 0.371, 6/16 0.381, 8/16 0.410 -- the loop
+      // is latency bound (issue 46-60 %, MUFU 40-64 %), see profiles/README.md.
+      constexpr uint32_t kEmuMask = (VARIANT == 1) ? 0u : (VARIANT == 3) ? 0x5252u : (VARIANT == 4) ? 0x5555u
+                                  : (VARIANT == 5) ? 0x9249u : 0x1111u;
+      const uint64_t c2 = f2_pack(c, c), nmc2 = f2_pack(-mc, -mc);
+      uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};  // independent packed row-sum chains
       uint32_t pk[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float x0 = fmaf(__uint_as_float(h ? s1[i] : s0[i]), c, -mc);
-          const float x1 = fmaf(__uint_as_float(h ? s1[i + 1] : s0[i + 1]), c, -mc);
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(h ? s1[i] : s0[i]), __uint_as_float(h ? s1[i + 1] : s0[i + 1])),
+                                     c2, nmc2);
           float p0, p1;
           if constexpr (VARIANT == 2 || VARIANT == 9) {
-            p0 = x0;
-            p1 = x1;
-          } else if constexpr (VARIANT == 1) {
-            p0 = fast_exp2(x0);
-            p1 = fast_exp2(x1);
+            f2_unpack(x2, p0, p1);
           } else {
-            // The exponentials are MUFU bound (clock64 timeline: 64 ex2 per thread take ~1235 cycles with two warps per
-            // scheduler = 1024 cycles of MUFU pipe). One pair in four goes to the FMA pipe instead; more than that and
-            // the extra ~9 instructions per element make the schedulers issue bound (measured: 3/8 gave no gain).
-            if (((i >> 1) & 3) == 3) {
-              p0 = exp2_fma(x0);
-              p1 = exp2_fma(x1);
+            if ((kEmuMask >> (i >> 1)) & 1u) {
+              exp2_fma2(x2, p0, p1);
             } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
           }
-          rs[(i >> 1) & 3] += p0;
-          rs[4 + ((i >> 1) & 3)] += p1;
+          rs2[(i >> 1) & 3] = f2_add(rs2[(i >> 1) & 3], f2_pack(p0, p1));
           pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
         }
       }
-      l_part += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(f2_add(rs2[0], rs2[1]), f2_add(rs2[2], rs2[3])), a0, a1);
+        b0 = a0 + a1;
+        (void)b1;
+        l_part += b0;
+      }
       stamp(j, 4);
       if (j > 0) {  // P(j-1) V(j-1) must have retired before P is overwritten / O may be rescaled
         mbar_wait(o_full, (j - 1) & 1, 0x570);

@@ -340,7 +340,8 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
   float sres = __ldg(aux + 32);
 #pragma unroll
   for (int i = 0; i < 32; ++i) sres = fmaf(fmaxf(acc[i], 0.f), __ldg(aux + i), sres);
-  if (apply_sigmoid) sres = 1.0f / (1.0f + __expf(-sres));
+  if (apply_sigmoid == 1) sres = 1.0f / (1.0f + __expf(-sres));
+  else if (apply_sigmoid == 2) sres = fmaxf(sres, 0.f);  // un-guided head ends in ReLU (depth_anything_v2_raw/dpt.py:115,182)
   out[(static_cast<long long>(b) * H + Y) * W + X] = sres;
 }
 

@@ -457,7 +457,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             v = fmaxf(v, 0.0f);
             s = fmaf(v, __ldg(g.aux + j), s);
           }
-          if (g.sigmoid) s = 1.0f / (1.0f + __expf(-s));
+          if (g.sigmoid == 1) s = 1.0f / (1.0f + __expf(-s));
+          else if (g.sigmoid == 2) s = fmaxf(s, 0.f);
           if (valid) g.out_f32[orow] = s;
         }
       } else {

@@ -320,6 +320,49 @@ __device__ __forceinline__ float exp2_fma(float x) {
   p = fmaf(p, f, 0.9999280735522232f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// ---- packed fp32 pairs (FFMA2 / FADD2, sm_100+): one issue slot for two lanes' worth of work. The softmax of the attention
+// kernel is issue-bound (ncu: 66 % issue-active, 7.8 instructions per score), so halving the FMA-pipe instruction count
+// is what buys time there.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// exp2_fma on a pair: same Cody-Waite split and degree-3 polynomial, FADD2/FFMA2 for the arithmetic.
+__device__ __forceinline__ void exp2_fma2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t xc = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t t2 = f2_add(xc, f2_pack(12582912.0f, 12582912.0f));
+  const uint64_t n2 = f2_add(t2, f2_pack(-12582912.0f, -12582912.0f));
+  const uint64_t f2 = f2_fma(n2, f2_pack(-1.0f, -1.0f), xc);
+  uint64_t p = f2_fma(f2, f2_pack(0.05517166769240653f, 0.05517166769240653f), f2_pack(0.24261112208902955f, 0.24261112208902955f));
+  p = f2_fma(p, f2, f2_pack(0.6932609857127241f, 0.6932609857127241f));
+  p = f2_fma(p, f2, f2_pack(0.9999280735522232f, 0.9999280735522232f));
+  float t0, t1, q0, q1;
+  f2_unpack(t2, t0, t1);
+  f2_unpack(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

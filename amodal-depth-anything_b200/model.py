@@ -51,8 +51,10 @@ class _Tree(nn.Module):
         self._modules[head].put(rest, tensor)
 
 
-def _param_table(cfg, guide_type):
-    """(name, shape, init-kind) for every tensor under `encoder.` in reference order of construction."""
+def _param_table(cfg, guide_type, input_projection=True):
+    """(name, shape, init-kind) for every tensor under `encoder.` in reference order of construction.
+    input_projection=False gives the un-guided DepthAnythingV2 of depth_anything_v2_raw/dpt.py (no guidance embed, no
+    input_projection levels)."""
     D, F, C = cfg["embed_dim"], cfg["features"], cfg["out_channels"]
     t = []
     p = "pretrained."
@@ -99,7 +101,7 @@ def _param_table(cfg, guide_type):
                 t += conv(r + f"resConfUnit{u}.conv{cv}", F, F, 3)
     t += conv("scratch.output_conv1", F // 2, F, 3) + conv("scratch.output_conv2.0", 32, F // 2, 3)
     t += conv("scratch.output_conv2.2", 1, 32, 1)
-    for i in range(4):
+    for i in range(4 if input_projection else 0):
         t += conv(f"input_projection.{i}.0", C[i], C[i], 3)
         t += [(h + f"input_projection.{i}.1.weight", (C[i],), "ones"), (h + f"input_projection.{i}.1.bias", (C[i],), "zeros")]
     return t
@@ -126,26 +128,22 @@ def _init(shape, kind):
     raise ValueError(kind)
 
 
-class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
-    def __init__(self, guide_type="image+mask", loss_stategy="invisible_part", encoder="vitg", pretrained=True):
-        super().__init__()
-        self.guide_type = guide_type
-        self.loss_stategy = loss_stategy
-        self.encoder_name = encoder
-        self.pretrained = pretrained
-        cfg = MODEL_CONFIGS[encoder]  # KeyError for unknown encoders, as the reference
-        if guide_type not in GUIDE_CHANNELS:
-            raise NotImplementedError  # dinov2.py:124-125
-        self._cfg = cfg
-        tree = _Tree()
-        for name, shape, kind in _param_table(cfg, guide_type):
-            tree.put(name, _init(shape, kind))
-        self.encoder = tree
-        self.register_buffer("pixel_mean", torch.Tensor([0.485, 0.456, 0.406]).view(-1, 1, 1), False)  # dav2.py:50
-        self.register_buffer("pixel_std", torch.Tensor([0.229, 0.224, 0.225]).view(-1, 1, 1), False)   # dav2.py:51
+class _NativeModel(nn.Module):
+    """Weight ownership + handle management shared by the two model classes: parameters live in torch (so .cuda(),
+    state_dict(), from_pretrained work as in the reference); a C-ABI handle holding the packed bf16 copies is (re)built
+    lazily whenever the parameters may have changed."""
+
+    def _native_init(self):
         self._handle = None
         self._handle_device = None
         self._dirty = True
+
+    # ---- subclass contract
+    def _native_config(self) -> dict:  # keys of L.AdaConfig
+        raise NotImplementedError
+
+    def _native_state(self) -> dict:   # reference keys relative to the inner net ("pretrained.*", "depth_head.*")
+        raise NotImplementedError
 
     # ------------------------------------------------------------------ weight ownership / repacking
     def _apply(self, fn, *a, **k):
@@ -176,7 +174,7 @@ class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
             return
         self._release()
         lib = L.load()
-        c = self._cfg
+        c = self._native_config()
         cfg = L.AdaConfig()
         cfg.embed_dim, cfg.depth, cfg.num_heads = c["embed_dim"], c["depth"], c["num_heads"]
         cfg.ffn_kind = 0 if c["ffn"] == "mlp" else 1
@@ -184,15 +182,17 @@ class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
         cfg.taps = (ctypes.c_int32 * 4)(*c["taps"])
         cfg.features = c["features"]
         cfg.out_channels = (ctypes.c_int32 * 4)(*c["out_channels"])
-        cfg.guide_channels = GUIDE_CHANNELS[self.guide_type]
-        cfg.sigmoid = 0 if "ssi" in self.loss_stategy else 1  # dpt.py:138-151
+        cfg.guide_channels = c["guide_channels"]
+        cfg.sigmoid = c["final_act"]
         cfg.pos_grid = POS_GRID
         cfg.interpolate_offset = 0.1
+        cfg.input_projection = c["input_projection"]
+        cfg.normalize_input = c["normalize_input"]
         h = ctypes.c_void_p()
         with torch.cuda.device(device):
             L.check(lib.ada_create(ctypes.byref(cfg), ctypes.byref(h)))
             try:
-                for key, p in self.encoder.state_dict().items():
+                for key, p in self._native_state().items():
                     t = p.detach().to(dtype=torch.float32).contiguous()
                     shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
                     L.check(lib.ada_set_weight(h, key.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()))
@@ -204,27 +204,14 @@ class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
         if getattr(self, "_capture", False):
             lib.ada_set_capture(h, 1)
 
-    # ------------------------------------------------------------------ forward
-    def _guides(self, guide_rgb, guide_mask, observation):
-        """dav2.py:67-82: which tensors are concatenated, in order. A required guide that is None raises TypeError
-        like torch.cat does in the reference."""
-        order = {"image+mask+observation": (guide_rgb, guide_mask, observation), "image+mask": (guide_rgb, guide_mask),
-                 "image+observation": (guide_rgb, observation), "mask+observation": (guide_mask, observation),
-                 "observation": (observation,), "mask": (guide_mask,), "none": ()}
-        if self.guide_type not in order:
-            raise NotImplementedError
-        gs = order[self.guide_type]
-        for g in gs:
-            if g is None:
-                raise TypeError("expected Tensor as element of the guide concatenation but got NoneType")
-        return list(gs)
-
-    def forward(self, x, guide_rgb=None, guide_mask=None, observation=None):
+    def _run(self, x, guides):
+        """x [B,3,H,W], guides: list of [B,c,H,W]; returns [B,1,H,W] fp32 on x's device, asynchronously on the current
+        stream."""
         if self.training:
-            raise RuntimeError("AmodalDAv2 (B200 path) is inference-only: call .eval() first; training is out of scope")
-        guides = self._guides(guide_rgb, guide_mask, observation)
+            raise RuntimeError(f"{type(self).__name__} (B200 path) is inference-only: call .eval() first; training is "
+                               "out of scope")
         if not x.is_cuda:
-            raise RuntimeError("AmodalDAv2 (B200 path) needs CUDA tensors: there is no CPU fallback")
+            raise RuntimeError(f"{type(self).__name__} (B200 path) needs CUDA tensors: there is no CPU fallback")
         B, C3, H, W = x.shape
         assert C3 == 3, "x must be [B,3,H,W]"
         assert H % 14 == 0, f"Input image height {H} is not a multiple of patch height 14"    # patch_embed.py:73
@@ -248,6 +235,7 @@ class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
                                          ctypes.c_void_p(out.data_ptr()), B, H, W, stream))
         return out
 
+
     # ------------------------------------------------------------------ test hooks
     def set_capture(self, on: bool):
         self._capture = bool(on)
@@ -265,11 +253,126 @@ class AmodalDAv2(nn.Module, PyTorchModelHubMixin):
     def workspace_bytes(self) -> int:
         return int(L.load().ada_workspace_bytes(self._handle)) if self._handle is not None else 0
 
+
+class AmodalDAv2(_NativeModel, PyTorchModelHubMixin):
+    def __init__(self, guide_type="image+mask", loss_stategy="invisible_part", encoder="vitg", pretrained=True):
+        super().__init__()
+        self.guide_type = guide_type
+        self.loss_stategy = loss_stategy
+        self.encoder_name = encoder
+        self.pretrained = pretrained
+        cfg = MODEL_CONFIGS[encoder]  # KeyError for unknown encoders, as the reference
+        if guide_type not in GUIDE_CHANNELS:
+            raise NotImplementedError  # dinov2.py:124-125
+        self._cfg = cfg
+        tree = _Tree()
+        for name, shape, kind in _param_table(cfg, guide_type):
+            tree.put(name, _init(shape, kind))
+        self.encoder = tree
+        self.register_buffer("pixel_mean", torch.Tensor([0.485, 0.456, 0.406]).view(-1, 1, 1), False)  # dav2.py:50
+        self.register_buffer("pixel_std", torch.Tensor([0.229, 0.224, 0.225]).view(-1, 1, 1), False)   # dav2.py:51
+        self._native_init()
+
+    def _native_config(self):
+        return dict(self._cfg, guide_channels=GUIDE_CHANNELS[self.guide_type],
+                    final_act=0 if "ssi" in self.loss_stategy else 1,  # dpt.py:138-151
+                    input_projection=1, normalize_input=1)
+
+    def _native_state(self):
+        return self.encoder.state_dict()
+
+    # ------------------------------------------------------------------ forward
+    def _guides(self, guide_rgb, guide_mask, observation):
+        """dav2.py:67-82: which tensors are concatenated, in order. A required guide that is None raises TypeError
+        like torch.cat does in the reference."""
+        order = {"image+mask+observation": (guide_rgb, guide_mask, observation), "image+mask": (guide_rgb, guide_mask),
+                 "image+observation": (guide_rgb, observation), "mask+observation": (guide_mask, observation),
+                 "observation": (observation,), "mask": (guide_mask,), "none": ()}
+        if self.guide_type not in order:
+            raise NotImplementedError
+        gs = order[self.guide_type]
+        for g in gs:
+            if g is None:
+                raise TypeError("expected Tensor as element of the guide concatenation but got NoneType")
+        return list(gs)
+
+    def forward(self, x, guide_rgb=None, guide_mask=None, observation=None):
+        if self.training:
+            raise RuntimeError("AmodalDAv2 (B200 path) is inference-only: call .eval() first; training is out of scope")
+        return self._run(x, self._guides(guide_rgb, guide_mask, observation))
+
     # ------------------------------------------------------------------ serialisation (dav2.py:87-90)
     def _save_pretrained(self, save_directory) -> None:
         from safetensors.torch import save_model as save_model_as_safetensor
         model_to_save = self.module if hasattr(self, "module") else self
         save_model_as_safetensor(model_to_save, str(save_directory / SAFETENSORS_SINGLE_FILE))
+
+
+class DepthAnythingV2(_NativeModel):
+    """Drop-in for the un-guided `DepthAnythingV2` of depth_anything_v2_raw/dpt.py:154-187 -- the "observation" model
+    infer.py:16-28,59-61 runs before the amodal model on every image. Same kernels as
+    AmodalDAv2 minus the guidance embedding and the input_projection levels; the head ends in ReLU
+    (depth_anything_v2_raw/dpt.py:109-116,182). Differences from the reference class: inference-only, CUDA-only,
+    `use_bn` / `use_clstoken` (both False everywhere in the reference) are not implemented.
+
+    forward(x): x [B,3,H,W] fp32, ALREADY ImageNet-normalised by the caller (infer.py:18) -> [B,H,W] fp32 >= 0."""
+
+    def __init__(self, encoder="vitg", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False,
+                 use_clstoken=False):
+        super().__init__()
+        if use_bn or use_clstoken:
+            raise NotImplementedError("use_bn / use_clstoken are not part of the B200 path")
+        self.encoder = encoder
+        enc = MODEL_CONFIGS[encoder]  # KeyError for unknown encoders (dpt.py:166-171 indexes intermediate_layer_idx)
+        self._cfg = dict(enc, features=int(features), out_channels=[int(c) for c in out_channels])
+        pre, head = _Tree(), _Tree()
+        for name, shape, kind in _param_table(self._cfg, "none", input_projection=False):
+            root, _, rest = name.partition(".")
+            (pre if root == "pretrained" else head).put(rest, _init(shape, kind))
+        self.pretrained = pre
+        self.depth_head = head
+        self._native_init()
+
+    def _native_config(self):
+        return dict(self._cfg, guide_channels=0, final_act=2, input_projection=0, normalize_input=0)
+
+    def _native_state(self):
+        return self.state_dict()
+
+    def forward(self, x):
+        return self._run(x, []).squeeze(1)  # depth_anything_v2_raw/dpt.py:181-184
+
+    # ---- host-side convenience of the reference class (depth_anything_v2_raw/dpt.py:186-222); glue, not the hot path
+    @staticmethod
+    def _input_size(h, w, target=518, multiple=14):
+        """Resize(keep_aspect_ratio, lower_bound, ensure_multiple_of=14) of util/transform.py:52-102."""
+        scale = max(target / h, target / w)
+
+        def fit(v):
+            y = int(round(scale * v / multiple) * multiple)
+            if y < target:
+                y = int(math.ceil(scale * v / multiple) * multiple)
+            return y
+        return fit(h), fit(w)
+
+    def image2tensor(self, raw_image, input_size=518):
+        import cv2
+        import numpy as np
+        h, w = raw_image.shape[:2]
+        image = cv2.cvtColor(raw_image, cv2.COLOR_BGR2RGB) / 255.0
+        nh, nw = self._input_size(h, w, input_size)
+        image = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_CUBIC)
+        image = (image - np.array([0.485, 0.456, 0.406])) / np.array([0.229, 0.224, 0.225])
+        image = np.ascontiguousarray(np.transpose(image, (2, 0, 1))).astype(np.float32)
+        dev = next(self.parameters()).device
+        return torch.from_numpy(image).unsqueeze(0).to(dev), (h, w)
+
+    @torch.no_grad()
+    def infer_image(self, raw_image, input_size=518):
+        image, (h, w) = self.image2tensor(raw_image, input_size)
+        depth = self.forward(image)
+        depth = torch.nn.functional.interpolate(depth[:, None], (h, w), mode="bilinear", align_corners=True)[0, 0]
+        return depth.cpu().numpy()
 
 
 def get_model(model_name, **kwargs):

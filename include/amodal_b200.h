@@ -38,9 +38,14 @@ typedef struct ada_config {
   int32_t features;          /* DPT feature width F                          dav2.py:32-34 */
   int32_t out_channels[4];   /* reassemble widths C_i                        dav2.py:32-34 */
   int32_t guide_channels;    /* channels of patch_embed_guidance (0 = 'none') dinov2.py:110-125 */
-  int32_t sigmoid;           /* 1 unless 'ssi' in loss_stategy               dpt.py:138-151 */
+  int32_t sigmoid;           /* final activation of output_conv2: 1 = Sigmoid (dpt.py:146-151), 0 = none ('ssi' in
+                                loss_stategy, dpt.py:138-144), 2 = ReLU (un-guided model, depth_anything_v2_raw/dpt.py:109-116,182) */
   int32_t pos_grid;          /* sqrt(num_patches) of pos_embed = 37          dinov2.py:437 */
   float interpolate_offset;  /* 0.1                                          dinov2.py:446 */
+  int32_t input_projection;  /* 1 = guided head: conv3x3 + channel LN + ReLU per level (dpt.py:153-159,178-179);
+                                0 = un-guided DepthAnythingV2 head (depth_anything_v2_raw/dpt.py:118-151) */
+  int32_t normalize_input;   /* 1 = rgb in [0,1], ImageNet (x-mean)/std applied inside (dav2.py:65);
+                                0 = caller passes the normalised image (depth_anything_v2_raw/dpt.py:168, infer.py:18) */
 } ada_config;
 
 /* ---- model lifetime -------------------------------------------------------------------------------------------- */

@@ -183,8 +183,10 @@ def feature_fusion(sd, pre: str, xs: List[torch.Tensor], size=None):
     return F.conv2d(out, sd[pre + "out_conv.weight"], sd[pre + "out_conv.bias"])
 
 
-def dpt_head(sd, cfg, feats, patch_h: int, patch_w: int, sigmoid: bool, inter: Optional[dict] = None):
-    """dpt.py:161-197 (use_clstoken=False)."""
+def dpt_head(sd, cfg, feats, patch_h: int, patch_w: int, sigmoid: bool, inter: Optional[dict] = None,
+             input_projection: bool = True):
+    """dpt.py:161-197 (use_clstoken=False). input_projection=False: the un-guided head of
+    depth_anything_v2_raw/dpt.py:118-151 (identical but for the missing input_projection levels)."""
     h = "encoder.depth_head."
     out = []
     for i, (x, _cls) in enumerate(feats):
@@ -199,8 +201,10 @@ def dpt_head(sd, cfg, feats, patch_h: int, patch_w: int, sigmoid: bool, inter: O
         out.append(x)
     layers = []
     for i, x in enumerate(out):                                                          # dpt.py:153-159,178-179
-        x = F.conv2d(x, sd[h + f"input_projection.{i}.0.weight"], sd[h + f"input_projection.{i}.0.bias"], padding=1)
-        x = F.relu(channel_layernorm(x, sd[h + f"input_projection.{i}.1.weight"], sd[h + f"input_projection.{i}.1.bias"]))
+        if input_projection:
+            x = F.conv2d(x, sd[h + f"input_projection.{i}.0.weight"], sd[h + f"input_projection.{i}.0.bias"], padding=1)
+            x = F.relu(channel_layernorm(x, sd[h + f"input_projection.{i}.1.weight"],
+                                         sd[h + f"input_projection.{i}.1.bias"]))
         layers.append(x)
     rn = [F.conv2d(layers[i], sd[h + f"scratch.layer{i + 1}_rn.weight"], None, padding=1) for i in range(4)]  # 184-187
     s = h + "scratch."
@@ -233,6 +237,19 @@ def forward(sd: Dict[str, torch.Tensor], encoder: str, guide_type: str, x, guide
         for i, (f, _c) in enumerate(feats):
             inter[f"tap{i}"] = f
     return dpt_head(sd, cfg, feats, patch_h, patch_w, sigmoid=("ssi" not in loss_stategy), inter=inter)
+
+
+@torch.no_grad()
+def forward_raw(sd: Dict[str, torch.Tensor], encoder: str, x, inter: Optional[dict] = None):
+    """Un-guided DepthAnythingV2.forward (depth_anything_v2_raw/dpt.py:176-184): x is the ImageNet-normalised image
+    (the caller normalises, infer.py:18); the head's Sequential ends in ReLU (:109-116) and forward applies ReLU again
+    (:182). sd uses the raw model's keys (`pretrained.*`, `depth_head.*`). Returns [B,H,W] fp32."""
+    sd = {"encoder." + k: v for k, v in sd.items()}
+    cfg = CONFIGS[encoder]
+    patch_h, patch_w = x.shape[-2] // 14, x.shape[-1] // 14
+    feats = intermediate_layers(sd, cfg, x, None, inter)
+    logits = dpt_head(sd, cfg, feats, patch_h, patch_w, sigmoid=False, inter=inter, input_projection=False)
+    return F.relu(F.relu(logits)).squeeze(1)
 
 
 def abs_relative_difference(output, target, valid_mask=None):

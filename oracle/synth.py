@@ -15,9 +15,12 @@ import torch
 from .amodal_oracle import CONFIGS, GUIDE_CHANNELS, POS_GRID
 
 
-def state_dict_shapes(encoder: str, guide_type: str) -> "OrderedDict[str, tuple]":
+def state_dict_shapes(encoder: str, guide_type: str, features=None, out_channels=None,
+                      input_projection: bool = True) -> "OrderedDict[str, tuple]":
+    """features / out_channels override the wrapper's per-encoder table (dav2.py:31-34) -- the un-guided model takes them
+    as constructor arguments (depth_anything_v2_raw/dpt.py:155-162) and has no input_projection."""
     c = CONFIGS[encoder]
-    D, F, C = c["embed_dim"], c["features"], c["out_channels"]
+    D, F, C = c["embed_dim"], features or c["features"], list(out_channels or c["out_channels"])
     s: "OrderedDict[str, tuple]" = OrderedDict()
     p = "encoder.pretrained."
     s[p + "cls_token"] = (1, 1, D)
@@ -79,7 +82,7 @@ def state_dict_shapes(encoder: str, guide_type: str) -> "OrderedDict[str, tuple]
     s[h + "scratch.output_conv2.0.bias"] = (32,)
     s[h + "scratch.output_conv2.2.weight"] = (1, 32, 1, 1)
     s[h + "scratch.output_conv2.2.bias"] = (1,)
-    for i in range(4):
+    for i in range(4 if input_projection else 0):
         s[h + f"input_projection.{i}.0.weight"] = (C[i], C[i], 3, 3)
         s[h + f"input_projection.{i}.0.bias"] = (C[i],)
         s[h + f"input_projection.{i}.1.weight"] = (C[i],)
@@ -87,14 +90,26 @@ def state_dict_shapes(encoder: str, guide_type: str) -> "OrderedDict[str, tuple]
     return s
 
 
-def make_state_dict(encoder: str, guide_type: str = "mask+observation", seed: int = 0, stress: bool = False):
+def make_state_dict_raw(encoder: str, features: int, out_channels, seed: int = 0, shift: float = 0.25):
+    """Seeded state dict of the un-guided DepthAnythingV2 (depth_anything_v2_raw/dpt.py:154-175): keys `pretrained.*` /
+    `depth_head.*` (no `encoder.` prefix, no guidance, no input_projection). The last bias is shifted so that most of the
+    ReLU output is positive, as a trained depth model's is (an all-zero output would make the relative bar vacuous)."""
+    sd = make_state_dict(encoder, "none", seed, False, features=features, out_channels=out_channels,
+                         input_projection=False)
+    sd = OrderedDict((k[len("encoder."):], v) for k, v in sd.items())
+    sd["depth_head.scratch.output_conv2.2.bias"] += shift
+    return sd
+
+
+def make_state_dict(encoder: str, guide_type: str = "mask+observation", seed: int = 0, stress: bool = False,
+                    features=None, out_channels=None, input_projection: bool = True):
     """Seeded fp32 CPU state dict. Distributions follow the reference's init in spirit (Linear ~N(0,.02),
     convs uniform(+-1/sqrt(fan_in)) = torch's default, dinov2.py:359-364) but biases, LayerNorm affines, LayerScale and
     the guidance conv are randomised so that every tensor influences the output. `stress=True` scales the last conv so
     the sigmoid output spans most of (0,1) (tolerance regime)."""
     g = torch.Generator().manual_seed(1000 + seed)
     sd = OrderedDict()
-    for k, shp in state_dict_shapes(encoder, guide_type).items():
+    for k, shp in state_dict_shapes(encoder, guide_type, features, out_channels, input_projection).items():
         if k.endswith("mask_token"):
             t = torch.zeros(shp)
         elif k.endswith("cls_token") or k.endswith("pos_embed"):

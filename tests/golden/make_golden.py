@@ -28,6 +28,13 @@ def import_reference():
     return AmodalDAv2, DepthAnythingV2
 
 
+def import_reference_raw():
+    """The un-guided `DepthAnythingV2` infer.py:13,59 uses for the observation depth."""
+    import_reference()
+    from src.models.amodalsynthdrive.depth_anything_v2_raw.dpt import DepthAnythingV2 as RawDepthAnythingV2
+    return RawDepthAnythingV2
+
+
 def hook_intermediates(net, store):
     """net: DepthAnythingV2. Records the tensors named in SURVEY.md section 4 (module-level parity points)."""
     dh = net.depth_head
@@ -77,12 +84,44 @@ CASES = [
 ]
 
 
+RAW_CASES = [
+    # name, encoder, features, out_channels, B, H, W, seed, shift of the last bias (-0.003: part of the output is clipped by ReLU)
+    ("raw_vits_70x98_b2", "vits", 64, [48, 96, 192, 384], 2, 70, 98, 11, 0.25),
+    ("raw_vits_84_clip", "vits", 64, [48, 96, 192, 384], 1, 84, 84, 12, -0.003),
+    ("raw_vitg_56_b1", "vitg", 384, [1536, 1536, 1536, 1536], 1, 56, 56, 13, 0.25),  # infer.py:59
+]
+
+
+def main_raw(only):
+    from oracle import synth
+    from oracle.amodal_oracle import normalize_rgb
+    Raw = import_reference_raw()
+    os.makedirs(os.path.join(ROOT, "tests", "golden", "raw"), exist_ok=True)
+    for name, enc, F_, C, B, H, W, seed, shift in RAW_CASES:
+        if only and name not in only:
+            continue
+        sd = synth.make_state_dict_raw(enc, F_, C, seed, shift)
+        net = Raw(encoder=enc, features=F_, out_channels=C).eval()
+        net.load_state_dict(sd, strict=True)
+        x = normalize_rgb(synth.make_inputs(B, H, W, seed)["x"])  # the caller normalises (infer.py:18)
+        with torch.no_grad():
+            out = net(x)
+        meta = dict(encoder=enc, features=F_, out_channels=C, B=B, H=H, W=W, seed=seed, shift=shift,
+                    torch=torch.__version__)
+        path = os.path.join(ROOT, "tests", "golden", "raw", name + ".npz")
+        np.savez_compressed(path, output=out.numpy().astype(np.float32), meta=np.array(repr(meta)))
+        print(name, "out range", float(out.min()), float(out.max()), "zeros", float((out == 0).float().mean()), "->",
+              os.path.getsize(path) // 1024, "KB", flush=True)
+
+
 def main():
     from oracle import synth
     from oracle.amodal_oracle import CONFIGS
     AmodalDAv2, DepthAnythingV2 = import_reference()
     torch.manual_seed(0)
     only = sys.argv[1:]
+    if only and not any(o in [c[0] for c in CASES] for o in only):
+        return
     for name, enc, gt, ls, B, H, W, seed, stress in CASES:
         if only and name not in only:
             continue
@@ -122,3 +161,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_raw(sys.argv[1:])

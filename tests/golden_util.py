@@ -14,8 +14,13 @@ def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
-def load_golden(name):
-    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+def raw_golden_names():
+    """Fixtures of the un-guided DepthAnythingV2 (tests/golden/raw/, make_golden.py:main_raw)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "raw", "*.npz")))
+
+
+def load_golden(name, sub=""):
+    z = np.load(os.path.join(GOLDEN_DIR, sub, name + ".npz"))
     meta = ast.literal_eval(str(z["meta"]))
     return meta, z
 

@@ -100,3 +100,29 @@ def test_pos_embed_interpolation_host_matches_reference_formula():
         rc = lib.ada_interp_pos_embed_host(ctypes.c_void_p(src.data_ptr()), 37, D, gh, gw, 0.1, ctypes.c_void_p(out.data_ptr()))
         assert rc == 0
         assert (out - ref).abs().max().item() < 1e-4, (gh, gw)  # N(0,1) table; size= variant would differ by ~0.4
+
+
+def test_unguided_model_mirrors_reference_class():
+    """pkg.DepthAnythingV2 = depth_anything_v2_raw/dpt.py:154-187 (the observation model of infer.py:59-61): state-dict
+    template without `encoder.` prefix, guidance or input_projection; same error conventions as AmodalDAv2."""
+    m = pkg.DepthAnythingV2(encoder="vits", features=64, out_channels=[48, 96, 192, 384])
+    want = {k[len("encoder."):]: v for k, v in
+            synth.state_dict_shapes("vits", "none", 64, [48, 96, 192, 384], input_projection=False).items()}
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want and not any("input_projection" in k or "guidance" in k for k in got)
+    m.load_state_dict(synth.make_state_dict_raw("vits", 64, [48, 96, 192, 384], 1), strict=True)
+    big = synth.state_dict_shapes("vitg", "none", 384, [1536] * 4, input_projection=False)   # infer.py:59
+    assert big["encoder.depth_head.scratch.layer1_rn.weight"] == (384, 1536, 3, 3)
+    with pytest.raises(KeyError):
+        pkg.DepthAnythingV2(encoder="vitx")
+    with pytest.raises(NotImplementedError):
+        pkg.DepthAnythingV2(encoder="vits", use_clstoken=True)
+    x = torch.rand(1, 3, 28, 28)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m.train()(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval()(x)
+    # Resize(keep_aspect_ratio, lower_bound, multiple of 14) of util/transform.py:52-102, values from the reference class
+    for hw, want_hw in (((480, 640), (518, 686)), ((1000, 518), (994, 518)), ((300, 900), (518, 1554)),
+                        ((777, 333), (1204, 518)), ((1080, 1920), (518, 924))):
+        assert pkg.DepthAnythingV2._input_size(*hw) == want_hw

@@ -6,7 +6,7 @@ import torch
 
 from oracle import amodal_oracle as O
 from oracle import synth
-from tests.golden_util import golden_names, load_golden, sample
+from tests.golden_util import golden_names, load_golden, raw_golden_names, sample
 
 # big encoders are exercised at small resolution; still the weights are generated in full
 HEAVY = {"vitl_70_b1", "vitg_56_b1"}
@@ -51,3 +51,17 @@ def test_patch_size_assert():
     sd = synth.make_state_dict("vits", "none", 0)
     with pytest.raises(AssertionError):
         O.forward(sd, "vits", "none", torch.rand(1, 3, 60, 70))
+
+
+@pytest.mark.parametrize("name", raw_golden_names())
+def test_oracle_raw_matches_reference_golden(name):
+    """Un-guided DepthAnythingV2 (depth_anything_v2_raw/dpt.py): oracle.forward_raw against the
+    output of the unmodified reference class on the same seeded weights/inputs."""
+    meta, z = load_golden(name, "raw")
+    sd = synth.make_state_dict_raw(meta["encoder"], meta["features"], meta["out_channels"], meta["seed"], meta["shift"])
+    x = O.normalize_rgb(synth.make_inputs(meta["B"], meta["H"], meta["W"], meta["seed"])["x"])
+    out = O.forward_raw(sd, meta["encoder"], x)
+    ref = torch.from_numpy(z["output"])
+    assert out.shape == ref.shape == (meta["B"], meta["H"], meta["W"])
+    assert (out >= 0).all()
+    assert (out - ref).abs().max().item() < 2e-5
