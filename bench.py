@@ -275,8 +275,17 @@ def main():
         # dominant kernel = gemm_tcgen05_kernel (linear + implicit-conv launches of the same kernel)
         g_ms, g_fl, g_n = msv[0] + msv[1], fl[0] + fl[1], ln[0] + ln[1]
         ach = g_fl / g_ms / 1e9
+        traffic, traffic_note = None, None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (never measured live)
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")))
+            if (a.encoder, a.size, a.batch) == ("vitl", 518, 32):
+                traffic = tj["mean_dram_bytes_per_launch"]
+                traffic_note = (f"mean over the 4 linear GEMMs of one encoder block (96 of {g_n // a.profile_steps} GEMM launches/"
+                                f"step), algorithmic {tj['mean_algorithmic_bytes_per_launch']} B/launch; {tj['source']}")
+        except Exception:  # noqa: BLE001
+            pass
         roof = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": g_fl / g_n, "avg_launch_ms": g_ms / g_n, "launches_per_step": g_n // a.profile_steps,
                 "share_of_step": g_ms / tot}
