@@ -334,7 +334,6 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
     ADA_ATT_ATTR(3);
     ADA_ATT_ATTR(4);
     ADA_ATT_ATTR(5);
-    ADA_ATT_ATTR(9);
 #undef ADA_ATT_ATTR
     ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
     attr_set = true;
@@ -342,8 +341,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, 128, 1}, box_kv[3] = {64, static_cast<uint32_t>(kAttKV), 1};
   CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
+  CUtensorMap tmkv = make_tmap_bf16(qkv, 3, dims, str, box_kv);
   uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
   CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
@@ -355,16 +355,17 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
+#define ADA_ATT_LAUNCH(V, SMEM) attention_tcgen05_kernel<V><<<grid, kAttThreads, SMEM, st>>>(tm, tmkv, tmo, a)
   switch (variant) {
-    case 1: attention_tcgen05_kernel<1><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 2: attention_tcgen05_kernel<2><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 3: attention_tcgen05_kernel<3><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 4: attention_tcgen05_kernel<4><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 5: attention_tcgen05_kernel<5><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 9: attention_tcgen05_kernel<9><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
-    case 10: attention_tcgen05_kernel<10><<<grid, kAttThreads, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0), st>>>(tm, tmo, a); break;
-    default: attention_tcgen05_kernel<0><<<grid, kAttThreads, kAttSmemBytes, st>>>(tm, tmo, a); break;
+    case 1: ADA_ATT_LAUNCH(1, kAttSmemBytes); break;
+    case 2: ADA_ATT_LAUNCH(2, kAttSmemBytes); break;
+    case 3: ADA_ATT_LAUNCH(3, kAttSmemBytes); break;
+    case 4: ADA_ATT_LAUNCH(4, kAttSmemBytes); break;
+    case 5: ADA_ATT_LAUNCH(5, kAttSmemBytes); break;
+    case 10: ADA_ATT_LAUNCH(10, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0)); break;
+    default: ADA_ATT_LAUNCH(0, kAttSmemBytes); break;
   }
+#undef ADA_ATT_LAUNCH
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }

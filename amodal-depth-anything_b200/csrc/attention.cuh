@@ -5,7 +5,8 @@
 // One CTA = 128 queries of one (image, head); Q/K/V are read in place from the [B, N, 3, H, 64] QKV GEMM output
 // through one 3-D TMA map (out-of-range tokens are zero-filled by the hardware).
 //   warp 0     : TMA producer (Q once, then a 2-stage K ring and a 2-stage V ring)
-//   warp 1     : tcgen05 issuer.  S = Q K^T  (128x128x64, both operands K-major)        -> TMEM cols [0,128)
+//   warp 1     : tcgen05 issuer, the whole warp converged with one elected lane per instruction (ptx.cuh umma_*_w).
+//                                 S = Q K^T  (128x128x64, both operands K-major)        -> TMEM cols [0,128)
 //                                 O += P V   (128x64x128, P from TMEM, V MN-major smem)  -> TMEM cols [192,256)
 //   warps 2..9 : softmax, EIGHT warps: every query row (= TMEM lane) is shared by two threads that each own 64 of the
 //                128 score columns (warps w and w+4 sit on the same TMEM lane quarter). The pair exchanges its partial
@@ -18,11 +19,12 @@
 // rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row's maximum grows by more than 2^8, which happens in the first
 // tile or two; p may then reach 256, harmless in fp32/bf16, and O / l is exact either way.
 // Two CTAs fit per SM (80 KB smem, 256 TMEM columns, 96 registers x 320 threads each).
-// Variants tried and measured on the same shape (B=32, N=1370, 16 heads; numbers in profiles/README.md): 64-key tiles
-// with S and P double-buffered (0.42 ms), two query tiles per CTA sharing K/V (0.49 ms), fp16-pair exponentials
-// (ex2.approx.f16x2 is issued as two MUFU.EX2.F16, no gain), against 0.38 ms for this kernel; MUFU sits at 61 % with the
-// two resident CTAs' non-exponential phases (row max + pair exchange, TMEM ld/st, waits: ~830 of ~2800 cycles per tile)
-// only partly overlapped.
+// Variants tried and measured on the same shape (B=32, N=1370, 16 heads; numbers and timelines in profiles/README.md):
+// 64-key tiles with S and P double-buffered (0.42 ms), two query tiles per CTA sharing K/V (0.49 ms), fp16-pair
+// exponentials (ex2.approx.f16x2 is issued as two MUFU.EX2.F16, no gain), two softmax groups ping-ponging 64-key tiles
+// with a shared running maximum (0.371 ms) or as two independent streams merged in the epilogue (0.384 ms), against
+// 0.368 ms for this kernel. Issue slots ~55 %, MUFU 40-64 %, tensor pipe ~31 %: no single pipe is saturated; the two
+// resident CTAs' fixed-latency phases (row max + pair exchange, TMEM ld/st, barrier round trips) only partly overlap.
 #pragma once
 #include "ptx.cuh"
 
@@ -41,10 +43,11 @@ struct AttArgs {
 };
 
 // VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = every exponential on MUFU, 2 = exponentials
-// replaced by a copy (timing skeleton only, wrong results), 9 = 2 + no K/V reloads, 10 = clock64 timeline of one thread.
+// replaced by a copy (timing skeleton only, wrong results), 3/4/5 = other FMA-pipe fractions, 10 = clock64 timeline.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap /*tmap_kv*/,
+                         const __grid_constant__ CUtensorMap tmap_out,
                          const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
@@ -125,21 +128,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+    const uint64_t dq = make_smem_desc_sw128(sQ, 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(sK, 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(sV, 0, 1024);
     auto issue_s = [&](int j) {
       const int s = j & 1;
       mbar_wait(k_full(s), (j >> 1) & 1, 0x520 + s);
       tc_fence_after();
-      if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sQ + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sK + s * 16384 + k * 32, 16, 1024);
-          umma_bf16_ss(tS, da, db, idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(k_empty(s));
-        umma_commit(s_full);
-      }
-      __syncwarp();
+      for (int k = 0; k < 4; ++k) umma_bf16_ss_w(tS, dq + 2 * k, dk0 + s * 1024 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+      umma_commit_w(k_empty(s));
+      umma_commit_w(s_full);
     };
     const bool tli = (VARIANT == 10) && lane == 0 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
     auto istamp = [&](int j, int k) {
@@ -160,16 +159,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       istamp(j, 3);
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
-      if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = 8 packed TMEM columns of P
-          const uint64_t db = make_smem_desc_sw128(sV + s * 16384 + kk * 2048, 0, 1024);
-          umma_bf16_ts(tO, tP + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(v_empty(s));
-        umma_commit(o_full);
-      }
-      __syncwarp();
+      for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA = 8 packed TMEM columns of P
+        umma_bf16_ts_w(tO, tP + kk * 8, dv0 + s * 1024 + kk * 128, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+      umma_commit_w(v_empty(s));
+      umma_commit_w(o_full);
       istamp(j, 4);
     }
   } else {

@@ -238,6 +238,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1 && cta_rank == 0) {
     // ------------------------------------------------------------ MMA issuer (leader CTA of the pair)
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, BN, 0, 0);
+    const uint64_t da0 = make_smem_desc_sw128(smem_base, 16, 1024);
+    const uint64_t db0 = make_smem_desc_sw128(smem_base + Cfg::kABytes, 16, 1024);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -249,27 +251,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase, 0x300 + stage);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+        {  // whole warp converged, one elected lane per tcgen05 instruction (ptx.cuh: umma_bf16_ss_w)
+          const uint32_t soff = static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);  // descriptor address units: 16 B
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaK * 2, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaK * 2, 16, 1024);
+            const uint64_t da = da0 + soff + k * (kUmmaK * 2 >> 4);
+            const uint64_t db = db0 + soff + k * (kUmmaK * 2 >> 4);
             if constexpr (CG == 2)
-              umma_bf16_ss_cg2(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_cg2_w(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             else
-              umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_w(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) {
-            umma_commit_cg2(empty_bar(stage), 0x3);                 // frees this smem slot in BOTH CTAs
-            if (kb == num_kb - 1) umma_commit_cg2(tfull_bar(acc), 0x3);  // accumulator complete, both epilogues
+            umma_commit_cg2_w(empty_bar(stage), 0x3);                 // frees this smem slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_cg2_w(tfull_bar(acc), 0x3);  // accumulator complete, both epilogues
           } else {
-            umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
-            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+            umma_commit_w(empty_bar(stage));                 // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) umma_commit_w(tfull_bar(acc));  // accumulator complete
           }
         }
-        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
