@@ -203,35 +203,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       const int m_row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM;
       const int n_row0 = nt * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+      // whole warp converged, one elected lane per instruction; the (tap, channel-chunk) walk of the implicit-GEMM conv is
+      // kept in counters instead of a division per K block.
+      int cc = 0, kx = 0, ky = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          if constexpr (CG == 2) {
-            const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
-            mbar_expect_tx_cluster(fb, Cfg::kStageBytes);
-            if (g.a_mode == A_CONV3X3) {
-              const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
-              const int ky = tap / 3, kx = tap % 3;
-              tma_load_4d_cg2(sa, &tmap_a, fb, cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
-            } else {
-              tma_load_2d_cg2(sa, &tmap_a, fb, kb * kBlockK, m_row0);
-            }
-            tma_load_2d_cg2(sb, &tmap_b, fb, kb * kBlockK, n_row0);
-          } else {
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            if (g.a_mode == A_CONV3X3) {
-              const int tap = kb / g.c_chunks, cc = kb % g.c_chunks;
-              const int ky = tap / 3, kx = tap % 3;
-              tma_load_4d(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
-            } else {
-              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_row0);
-            }
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_row0);
-          }
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
+        if constexpr (CG == 2) {
+          const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+          mbar_expect_tx_cluster_w(fb, Cfg::kStageBytes);
+          if (g.a_mode == A_CONV3X3)
+            tma_load_4d_cg2_w(sa, &tmap_a, fb, cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+          else
+            tma_load_2d_cg2_w(sa, &tmap_a, fb, kb * kBlockK, m_row0);
+          tma_load_2d_cg2_w(sb, &tmap_b, fb, kb * kBlockK, n_row0);
+        } else {
+          mbar_expect_tx_w(full_bar(stage), Cfg::kStageBytes);
+          if (g.a_mode == A_CONV3X3)
+            tma_load_4d_w(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+          else
+            tma_load_2d_w(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_row0);
+          tma_load_2d_w(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_row0);
         }
-        __syncwarp();
+        if (++cc == g.c_chunks) {
+          cc = 0;
+          if (++kx == 3) { kx = 0; ++ky; }
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }

@@ -194,6 +194,46 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- whole-warp (elected lane) producer instructions: same reasoning as umma_bf16_ss_w -- the warp stays converged so the
+// compiler keeps addresses / coordinates in uniform registers instead of building R2UR waterfalls inside `if (lane == 0)`.
+#define ADA_ELECT_ASM(body) "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e " body "\n\t}"
+__device__ __forceinline__ void mbar_expect_tx_w(uint32_t bar, uint32_t bytes) {
+  asm volatile(ADA_ELECT_ASM("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;") ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster_w(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile(ADA_ELECT_ASM("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;") ::"r"(cluster_bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(ADA_ELECT_ASM(
+                   "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];")
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      ADA_ELECT_ASM(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];")
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_w(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      ADA_ELECT_ASM("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+                    "%4}], [%2];")
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2_w(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1,
+                                                  int c2, int c3) {
+  asm volatile(
+      ADA_ELECT_ASM("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+                    "%4, %5, %6}], [%2];")
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05.mma (bf16 x bf16 -> fp32, cta_group::1)
 // Shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell). Addresses/offsets in 16-byte units.
 //   K-major operand : rows of 128 B (64 bf16 of K); 8-row groups `sbo_bytes` apart (1024 when dense).

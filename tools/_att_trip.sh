@@ -1,3 +1,8 @@
-timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k attention 2>&1 | tail -3
-for v in 0 1 3 2; do ADA_ATT_VARIANT=$v timeout 60 python tools/bench_attention.py 2>&1 | tail -1; done
-ADA_ATT_VARIANT=0 N=5477 B=4 timeout 60 python tools/bench_attention.py 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu-baseline --detail gpurun_out/detail.json 2>&1 | tail -1 > gpurun_out/bench_w.json; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_w.json').read())
+print(d['value'], d['ms_per_step'], {k:(round(v['ms_per_step'],2)) for k,v in d['breakdown'].items()})
+for r in json.load(open("gpurun_out/detail.json"))[:24]:
+    print(f"{r['ms_per_step']:8.3f} ms/step  x{r['launches']:3d}  avg {r['avg_ms']:.3f} ms  {r['tflops'] or 0:7.1f} TF/s  {r['sig']}")
+PY
