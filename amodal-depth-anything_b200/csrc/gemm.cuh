@@ -97,16 +97,22 @@ struct GemmCfg {
 
 // GELU with the exact-erf definition (nn.GELU default, mlp.py:30-41): gelu(x) = x * Phi(x). Phi is evaluated as
 // sigmoid(x * q(x^2)) with q a degree-2 minimax fit (scipy, x in [-8, 8]) of logit(Phi(x)) / x:
-//   max |approx - x * 0.5 * (1 + erf(x / sqrt 2))| = 2.5e-5, below half a bf16 ulp of any stored value above 6e-3.
-// 6 FMA-pipe ops + 1 ALU op + 2 MUFU per element; the epilogue is FP32-issue bound (3-register FMA-pipe ops issue every
-// other cycle), and the previous Abramowitz-Stegun form (~22 ops) kept fc1 at 666 TFLOP/s vs 1221 for the plain epilogue.
-__device__ __forceinline__ float gelu_erf(float x) {
-  constexpr float kL2e = 1.4426950408889634f;
-  const float s = fminf(x * x, 50.0f);  // q is monotone on [0, 52]; beyond |x| = 7 the sigmoid is saturated anyway
-  float q = fmaf(-0.0007030335770476013f * -kL2e, s, 0.07401129204396431f * -kL2e);
-  q = fmaf(q, s, 1.5950157685717141f * -kL2e);
-  const float e = fast_exp2(x * q);    // exp(-x q(x^2))
-  return x * fast_rcp(1.0f + e);
+//   max |approx - x * 0.5 * (1 + erf(x / sqrt 2))| = 2.5e-5 for the fit itself.
+// sigmoid(z) = 0.5 + 0.5 tanh(z / 2) turns the two MUFU ops (ex2, rcp) into one (tanh.approx, relative error 2^-11, i.e.
+// <= 2.4e-4 |x| on the result -- a quarter of a bf16 ulp of the stored activation), and the arithmetic runs on packed
+// fp32 pairs: 5 issue slots per element instead of 9. The epilogue warps share their schedulers with the TMA and MMA
+// issuing warps, so epilogue issue slots are what fc1 (K = 1024) is short of.
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+  float s0, s1;
+  f2_unpack(f2_mul(x2, x2), s0, s1);
+  const uint64_t s2 = f2_pack(fminf(s0, 50.0f), fminf(s1, 50.0f));  // q is monotone on [0, 52]; tanh is saturated beyond
+  uint64_t q = f2_fma(f2_pack(-0.0007030335770476013f * 0.5f, -0.0007030335770476013f * 0.5f), s2,
+                      f2_pack(0.07401129204396431f * 0.5f, 0.07401129204396431f * 0.5f));
+  q = f2_fma(q, s2, f2_pack(1.5950157685717141f * 0.5f, 1.5950157685717141f * 0.5f));
+  float z0, z1;
+  f2_unpack(f2_mul(x2, q), z0, z1);  // x q(x^2) / 2
+  const uint64_t hx = f2_mul(x2, f2_pack(0.5f, 0.5f));
+  return f2_fma(hx, f2_pack(fast_tanh(z0), fast_tanh(z1)), hx);
 }
 
 __device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4 rr) {
@@ -330,8 +336,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         named_bar_sync(1, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;
-          s_bias[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
-          s_gamma[i] = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
+          const float bv = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
+          const float gv = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
+          s_bias[i] = (EPI == EPI_BF16) ? bv * gv : bv;  // EPI_BF16 applies (acc + b) * gamma as fma(acc, gamma, b * gamma)
+          s_gamma[i] = gv;
         }
         named_bar_sync(1, kEpiThreads);
       }
@@ -380,17 +388,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float* gg = s_gamma + cg * 64 + h * 32;
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
-                  float v[8];
+                  // (acc + bias) * gamma as one packed FMA per pair: the staged bias is already multiplied by gamma
+                  uint64_t v2[4];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gi * 8 + j]) + bb[gi * 8 + j];
-                  if (g.gamma != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] *= gg[gi * 8 + j];
+                  for (int j = 0; j < 4; ++j) {
+                    const uint64_t a2 = f2_pack(__uint_as_float(r[gi * 8 + 2 * j]), __uint_as_float(r[gi * 8 + 2 * j + 1]));
+                    const uint64_t b2 = *reinterpret_cast<const uint64_t*>(bb + gi * 8 + 2 * j);
+                    v2[j] = (g.gamma != nullptr) ? f2_fma(a2, *reinterpret_cast<const uint64_t*>(gg + gi * 8 + 2 * j), b2)
+                                                 : f2_add(a2, b2);
                   }
                   if (g.act == ACT_GELU) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-                  } else if (g.act == ACT_RELU) {
+                    for (int j = 0; j < 4; ++j) v2[j] = gelu_erf2(v2[j]);
+                  }
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) f2_unpack(v2[j], v[2 * j], v[2 * j + 1]);
+                  if (g.act == ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
                   }
