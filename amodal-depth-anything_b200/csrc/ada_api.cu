@@ -373,12 +373,12 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
 static void launch_channel_ln_relu(const __nv_bfloat16* in, const float* w, const float* b, __nv_bfloat16* out,
                                    long long pixels, int C, float eps, cudaStream_t st) {
   ADA_REQUIRE(C % 8 == 0 && C <= 1536, "channel LN: C % 8 == 0 and C <= 1536");
-  const int grid = static_cast<int>((pixels + 7) / 8);
+  const int grid = static_cast<int>(std::min<long long>((pixels + 15) / 16, 148LL * 8));  // persistent warps, 2 pixels in flight
   ProfScope prof(PC_CHANNEL_LN, 0.0, 4.0 * pixels * static_cast<double>(C), st);
   if (C <= 512)
-    channel_ln_relu_kernel<2><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+    channel_ln_relu_kernel<2, true><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
   else
-    channel_ln_relu_kernel<6><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+    channel_ln_relu_kernel<6, false><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
@@ -392,8 +392,8 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
   int shift = -1;
   for (int sft = 0; sft < 12; ++sft)
     if ((1 << sft) == groups) shift = sft;
-  dim3 grid(static_cast<unsigned>((static_cast<long long>(Wo) * groups + 255) / 256), static_cast<unsigned>(Ho),
-            static_cast<unsigned>(B));
+  dim3 grid(static_cast<unsigned>((static_cast<long long>(Wo) * groups + 255) / 256),
+            static_cast<unsigned>((Ho + kUpRows - 1) / kUpRows), static_cast<unsigned>(B));
   (void)total;
   upsample_bilinear_kernel<<<grid, 256, 0, st>>>(in, out, Hi, Wi, Ho, Wo, C, shift);
   ADA_CHECK_CUDA(cudaGetLastError());
@@ -1126,7 +1126,22 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
     e.epi = EPI_BF16;
     e.out_bf16 = m->vtap;
     e.ldo = 288;
-    linear(m->oc1b, B * ph[1] * pw[1], F / 2, F / 2, m->w_tail_taps, 288, F / 2, e, st);
+    {
+      // N = 288: three 128-wide column tiles (auto). Forcing 256 (two tiles, the second mostly padding) measured slower
+      // (1.21 vs 0.95 ms at batch 32); ADA_TAIL_BN overrides for experiments.
+      static const int tail_bn = env_int("ADA_TAIL_BN", 0);
+      GemmLaunch L;
+      L.A = m->oc1b;
+      L.Bw = m->w_tail_taps;
+      L.M = B * ph[1] * pw[1];
+      L.N = 288;
+      L.K = F / 2;
+      L.lda = F / 2;
+      L.ldb = F / 2;
+      L.args = e;
+      L.force_bn = tail_bn;
+      launch_gemm(L, st);
+    }
     launch_tail_gather(m->vtap, m->oc2.b, m->tail_aux, out, B, ph[1], pw[1], H, W, c.sigmoid, st);
   } else {
     launch_upsample(m->oc1b, m->up, B, ph[1], pw[1], H, W, F / 2, st);
