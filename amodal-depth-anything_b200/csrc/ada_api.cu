@@ -305,15 +305,18 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ other launchers
-static void launch_layernorm(float* x, const __nv_bfloat16* delta, const float* w, const float* b, __nv_bfloat16* out,
-                             int rows, int D, float eps, int n_tok, int drop_cls, int write_x, cudaStream_t st) {
+static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bfloat16* delta2, const float* w, const float* b,
+                             __nv_bfloat16* out, int rows, int D, float eps, int n_tok, int drop_cls, int write_x,
+                             cudaStream_t st) {
   const int grid = (rows + 7) / 8;
-  ProfScope prof(PC_LAYERNORM, 0.0, (6.0 + (delta ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0)) * rows * static_cast<double>(D), st);
+  ADA_REQUIRE(delta != nullptr || delta2 == nullptr, "layernorm: delta2 without delta");
+  ProfScope prof(PC_LAYERNORM, 0.0,
+                 (6.0 + (delta ? 2.0 : 0.0) + (delta2 ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0)) * rows * static_cast<double>(D), st);
   switch (D / 128) {
-    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, delta, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
     default: throw AdaError(ADA_EINVAL, "layernorm: embed_dim must be 384/768/1024/1536");
   }
   ADA_REQUIRE(D % 128 == 0, "layernorm: D % 128");
@@ -602,7 +605,7 @@ struct ada_model {
   std::unordered_map<std::string, int> named_is_f32;
   // buffers
   float* x = nullptr;
-  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *ybuf = nullptr, *a_embed = nullptr;
+  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *ybuf = nullptr, *ybuf2 = nullptr, *a_embed = nullptr;
   __nv_bfloat16* tap[4] = {};
   float* tokens_dbg = nullptr;
   __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *col4 = nullptr, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
@@ -848,6 +851,7 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
   m->att = b.take<__nv_bfloat16>(M * D);
   m->hbuf = b.take<__nv_bfloat16>(M * c.ffn_hidden);
   m->ybuf = b.take<__nv_bfloat16>(M * D);
+  m->ybuf2 = b.take<__nv_bfloat16>(M * D);
   m->a_embed = b.take<__nv_bfloat16>(BP * m->kpad);
   m->tokens_dbg = b.take<float>(M * D);
   reg("tokens", m->tokens_dbg, M * D, 1);
@@ -989,13 +993,14 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
     ADA_CHECK_CUDA(cudaMemcpyAsync(m->tokens_dbg, m->x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, st));
 
   // ---- encoder blocks (block.py:82-107 eval branch). The fp32 stream x is only touched by the LayerNorm kernel:
-  //      each residual branch leaves gamma * (W h + b) in `ybuf` (bf16) and the NEXT LayerNorm folds it in
-  //      (x <- x + ybuf, block.py:105-106) before normalising.
+  //      the attention branch leaves gamma1 * (W h + b) in `ybuf` and the MLP branch gamma2 * (...) in `ybuf2` (bf16).
+  //      norm2 normalises x + ybuf without storing it; the NEXT block's norm1 (or the tap norm) adds both and norm1
+  //      stores x <- (x + ybuf) + ybuf2 (block.py:105-106): one fp32 write of the stream per block.
   int tap_i = 0;
-  const __nv_bfloat16* pending = nullptr;  // residual-branch output not yet added to x
+  const __nv_bfloat16 *pend1 = nullptr, *pend2 = nullptr;  // residual-branch outputs not yet added to x
   for (int i = 0; i < c.depth; ++i) {
     const BlockW& w = m->blocks[i];
-    launch_layernorm(m->x, pending, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 1, st);
+    launch_layernorm(m->x, pend1, pend2, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 1, st);
     {
       GemmArgs e{};
       e.epi = EPI_BF16;
@@ -1014,7 +1019,7 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
       e.ldo = D;
       linear(m->att, M, D, D, w.wproj, D, D, e, st);
     }
-    launch_layernorm(m->x, m->ybuf, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 1, st);
+    launch_layernorm(m->x, m->ybuf, nullptr, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 0, st);
     const int Hd = c.ffn_hidden;
     {
       GemmArgs e{};
@@ -1035,15 +1040,16 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
       e.epi = EPI_BF16;
       e.bias = w.b2;
       e.gamma = w.g2;
-      e.out_bf16 = m->ybuf;
+      e.out_bf16 = m->ybuf2;
       e.ldo = D;
       linear(m->hbuf, M, Hd, Hd, w.w2, D, Hd, e, st);
     }
-    pending = m->ybuf;
+    pend1 = m->ybuf;
+    pend2 = m->ybuf2;
     if (tap_i < 4 && i == c.taps[tap_i]) {
-      // shared final norm of (x + pending), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is updated by
-      // the next block's first LayerNorm, so nothing is written back here
-      launch_layernorm(m->x, pending, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
+      // shared final norm of (x + both branches), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is updated
+      // by the next block's first LayerNorm, so nothing is written back here
+      launch_layernorm(m->x, pend1, pend2, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
       ++tap_i;
     }
   }
@@ -1413,12 +1419,14 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
   });
 }
 
-int ada_op_layernorm(float* x, const void* delta_bf16, const float* w, const float* b, void* out_bf16, int32_t rows,
-                     int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x, void* stream) {
+int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, const float* w, const float* b,
+                     void* out_bf16, int32_t rows, int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x,
+                     void* stream) {
   return guarded([&] {
     require_device();
-    launch_layernorm(x, static_cast<const __nv_bfloat16*>(delta_bf16), w, b, static_cast<__nv_bfloat16*>(out_bf16), rows, D,
-                     eps, n_tok, drop_cls, write_x, static_cast<cudaStream_t>(stream));
+    launch_layernorm(x, static_cast<const __nv_bfloat16*>(delta_bf16), static_cast<const __nv_bfloat16*>(delta2_bf16), w, b,
+                     static_cast<__nv_bfloat16*>(out_bf16), rows, D, eps, n_tok, drop_cls, write_x,
+                     static_cast<cudaStream_t>(stream));
   });
 }
 

@@ -16,14 +16,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reference: nn.LayerNorm(D, eps=1e-6) block.py:84,87 and the shared final norm dinov2.py:337-338.
 // drop_cls != 0: input rows are [B, n_tok, D]; token 0 (cls) is skipped and the output is the dense patch map
 // [B, n_tok-1, D] == NHWC [B, h, w, D] (dinov2.py:339-340 + dpt.py:168-171 collapse into the store address).
-// delta != nullptr: the pending residual-branch output (bf16, already LayerScale'd by the GEMM epilogue) is added
-// first, x <- x + delta (block.py:105-106), and written back when write_x is set; the fp32 stream is therefore only
-// ever touched by this coalesced kernel, never by the (row-per-thread) GEMM epilogue.
+// delta / delta2 != nullptr: the pending residual-branch outputs (bf16, already LayerScale'd by the GEMM epilogue) are
+// added first, x <- (x + delta) + delta2 (block.py:105-106), and written back when write_x is set; the fp32 stream is
+// therefore only ever touched by this coalesced kernel, never by the (row-per-thread) GEMM epilogue. The encoder writes
+// x once per block: norm2 normalises x + attn-branch without storing it, the next norm1 adds both branches and stores
+// (22 instead of 24 bytes per element and block).
 template <int CHUNKS>  // D = CHUNKS * 128
 __global__ void __launch_bounds__(256)
-layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const float* __restrict__ w,
-                      const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok,
-                      int drop_cls, int write_x) {
+layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                      const __nv_bfloat16* __restrict__ delta2, const float* __restrict__ w, const float* __restrict__ b,
+                      __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls, int write_x) {
   constexpr int D = CHUNKS * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -45,6 +47,14 @@ layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ d
     for (int i = 0; i < CHUNKS; ++i) {
       const uint2 d = dr[lane + 32 * i];
       v[i].x += bf16_lo(d.x); v[i].y += bf16_hi(d.x); v[i].z += bf16_lo(d.y); v[i].w += bf16_hi(d.y);
+    }
+    if (delta2 != nullptr) {
+      const uint2* er = reinterpret_cast<const uint2*>(delta2 + static_cast<long long>(row) * D);
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const uint2 d = er[lane + 32 * i];
+        v[i].x += bf16_lo(d.x); v[i].y += bf16_hi(d.x); v[i].z += bf16_lo(d.y); v[i].w += bf16_hi(d.y);
+      }
     }
     if (write_x) {
 #pragma unroll
@@ -332,9 +342,9 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
   const int ty = tid >> 4, tx = tid & 15;
   const int Y = Y0 + ty, X = X0 + tx;
   if (Y >= H || X >= W) return;
-  float acc[32];
+  uint64_t acc2[16];  // 32 fp32 accumulators as packed pairs (FFMA2: the kernel is issue bound, ~2300 instructions per pixel)
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = __ldg(bias2 + i);
+  for (int i = 0; i < 16; ++i) acc2[i] = f2_pack(__ldg(bias2 + 2 * i), __ldg(bias2 + 2 * i + 1));
   // per-tap source columns (three of them), rows handled in the loop
   int xo0[3], xo1[3];
   float lxv[3];
@@ -367,22 +377,21 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
 #pragma unroll
       for (int cnr = 0; cnr < 4; ++cnr) {
         const uint4* p = reinterpret_cast<const uint4*>(tail_smem + pidx[cnr] * kTailPitch + tap * 64);
-        const float wv = wgt[cnr];
+        const uint64_t wv2 = f2_pack(wgt[cnr], wgt[cnr]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 v = p[q];
-          acc[q * 8 + 0] = fmaf(wv, bf16_lo(v.x), acc[q * 8 + 0]);
-          acc[q * 8 + 1] = fmaf(wv, bf16_hi(v.x), acc[q * 8 + 1]);
-          acc[q * 8 + 2] = fmaf(wv, bf16_lo(v.y), acc[q * 8 + 2]);
-          acc[q * 8 + 3] = fmaf(wv, bf16_hi(v.y), acc[q * 8 + 3]);
-          acc[q * 8 + 4] = fmaf(wv, bf16_lo(v.z), acc[q * 8 + 4]);
-          acc[q * 8 + 5] = fmaf(wv, bf16_hi(v.z), acc[q * 8 + 5]);
-          acc[q * 8 + 6] = fmaf(wv, bf16_lo(v.w), acc[q * 8 + 6]);
-          acc[q * 8 + 7] = fmaf(wv, bf16_hi(v.w), acc[q * 8 + 7]);
+          acc2[q * 4 + 0] = f2_fma(wv2, f2_pack(bf16_lo(v.x), bf16_hi(v.x)), acc2[q * 4 + 0]);
+          acc2[q * 4 + 1] = f2_fma(wv2, f2_pack(bf16_lo(v.y), bf16_hi(v.y)), acc2[q * 4 + 1]);
+          acc2[q * 4 + 2] = f2_fma(wv2, f2_pack(bf16_lo(v.z), bf16_hi(v.z)), acc2[q * 4 + 2]);
+          acc2[q * 4 + 3] = f2_fma(wv2, f2_pack(bf16_lo(v.w), bf16_hi(v.w)), acc2[q * 4 + 3]);
         }
       }
     }
   }
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f2_unpack(acc2[i], acc[2 * i], acc[2 * i + 1]);
   float sres = __ldg(aux + 32);
 #pragma unroll
   for (int i = 0; i < 32; ++i) sres = fmaf(fmaxf(acc[i], 0.f), __ldg(aux + i), sres);

@@ -45,13 +45,13 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
     L.check(lib.ada_op_gemm(ctypes.byref(d), _stream()))
 
 
-def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=False):
+def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=False, delta2=None):
     rows, D = x.shape
     if drop_cls:
         out = torch.empty((rows // n_tok) * (n_tok - 1), D, dtype=torch.bfloat16, device=x.device)
     else:
         out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
-    L.check(L.load().ada_op_layernorm(_p(x), _p(delta), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls),
+    L.check(L.load().ada_op_layernorm(_p(x), _p(delta), _p(delta2), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls),
                                       int(write_x), _stream()))
     return out
 

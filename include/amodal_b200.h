@@ -117,10 +117,12 @@ typedef struct ada_gemm_desc {
   int32_t force_cg;     /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
-/* out[rows or B*(n_tok-1), D] bf16 = LayerNorm(x + delta) (block.py:84,87,105-106; dinov2.py:337-340 when drop_cls).
- * x fp32 [rows, D]; delta (optional, bf16 [rows, D]) is the pending residual-branch output; write_x stores x + delta back. */
-int ada_op_layernorm(float* x, const void* delta_bf16, const float* w, const float* b, void* out_bf16, int32_t rows,
-                     int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x, void* stream);
+/* out[rows or B*(n_tok-1), D] bf16 = LayerNorm((x + delta) + delta2) (block.py:84,87,105-106; dinov2.py:337-340 when
+ * drop_cls). x fp32 [rows, D]; delta / delta2 (optional, bf16 [rows, D]) are the pending residual-branch outputs (delta2
+ * requires delta); write_x stores the sum back into x. */
+int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, const float* w, const float* b,
+                     void* out_bf16, int32_t rows, int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x,
+                     void* stream);
 /* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
 int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
 /* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */

@@ -191,6 +191,15 @@ def chk_layernorm_delta():
     r["x_written"] = bool(torch.equal(x1, xs))
     r["x_untouched"] = bool(torch.equal(x2, x))
     r["ok"] = r["ok"] and r["x_written"] and r["x_untouched"] and bool(torch.equal(out, out2))
+    # two pending branches: (x + d) + d2, the order the encoder relies on (norm2 sees x + d, the next norm1 adds d2)
+    d2 = torch.randn(rows, D, generator=g, device="cuda").bfloat16()
+    x3 = x.clone()
+    out3 = ops.layernorm(x3, w, b, 1e-6, 1, False, delta=d, write_x=True, delta2=d2)
+    torch.cuda.synchronize()
+    xs2 = (x + d.float()) + d2.float()
+    r2 = _cmp("ln2", out3, torch.nn.functional.layer_norm(xs2, (D,), w, b, 1e-6), 2e-2, 1e-2)
+    r["x_written_2"] = bool(torch.equal(x3, xs2))
+    r["ok"] = r["ok"] and r2["ok"] and r["x_written_2"]
     return r
 
 
