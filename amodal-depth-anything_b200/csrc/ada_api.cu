@@ -18,6 +18,7 @@
 #include "../../include/amodal_b200.h"
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "postproc.cuh"
 #include "gemm.cuh"
 #include "tma_host.h"
 
@@ -1427,6 +1428,52 @@ int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, 
     launch_layernorm(x, static_cast<const __nv_bfloat16*>(delta_bf16), static_cast<const __nv_bfloat16*>(delta2_bf16), w, b,
                      static_cast<__nv_bfloat16*>(out_bf16), rows, D, eps, n_tok, drop_cls, write_x,
                      static_cast<cudaStream_t>(stream));
+  });
+}
+
+// ---- single-image pre/post-processing of infer.py
+int ada_pre_image_nearest(const uint8_t* img_hwc, int32_t H0, int32_t W0, float* out_chw, int32_t H, int32_t W,
+                          int32_t normalize, void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(img_hwc && out_chw && H0 > 0 && W0 > 0 && H > 0 && W > 0, "bad argument");
+    image_nearest_kernel<<<(H * W + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(img_hwc, H0, W0, out_chw, H, W, normalize);
+    ADA_CHECK_CUDA(cudaGetLastError());
+  });
+}
+
+int ada_pre_mask_nearest(const uint8_t* mask, int32_t H0, int32_t W0, float* mask01, float* guide, int32_t H, int32_t W,
+                         void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(mask && (mask01 || guide) && H0 > 0 && W0 > 0 && H > 0 && W > 0, "bad argument");
+    mask_nearest_kernel<<<(H * W + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, H0, W0, mask01, guide, H, W);
+    ADA_CHECK_CUDA(cudaGetLastError());
+  });
+}
+
+int ada_post_minmax_normalize(const float* depth, int64_t n, float* base01, float* obs, void* scratch8, void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(depth && (base01 || obs) && scratch8 && n > 0, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* mm = static_cast<uint32_t*>(scratch8);
+    const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 8));
+    minmax_init_kernel<<<1, 1, 0, st>>>(mm);
+    minmax_kernel<<<grid, 256, 0, st>>>(depth, n, mm);
+    normalize_kernel<<<grid, 256, 0, st>>>(depth, n, mm, base01, obs);
+    ADA_CHECK_CUDA(cudaGetLastError());
+  });
+}
+
+int ada_post_blend_seam(const float* raw01, const float* amodal, const float* mask01, float* out, int32_t H, int32_t W,
+                        void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(raw01 && amodal && mask01 && out && H > 1 && W > 1, "bad argument");
+    ADA_REQUIRE(out != raw01 && out != amodal, "blend_seam is not in-place safe");
+    blend_seam_kernel<<<(H * W + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(raw01, amodal, mask01, out, H, W);
+    ADA_CHECK_CUDA(cudaGetLastError());
   });
 }
 

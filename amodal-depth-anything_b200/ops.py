@@ -128,3 +128,41 @@ def tail_gather(V, bias2, aux, H, W, sigmoid=True):
     out = torch.empty(B, H, W, dtype=torch.float32, device=V.device)
     L.check(L.load().ada_op_tail_gather(_p(V), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, int(sigmoid), _stream()))
     return out
+
+
+# ---- single-image pre/post-processing of infer.py (include/amodal_b200.h, "row f2")
+def image_nearest(img_u8_hwc, H=518, W=518, normalize=False):
+    """uint8 [H0,W0,3] (device) -> fp32 [1,3,H,W]; infer.py:84-86 (normalize=True: infer.py:18)."""
+    H0, W0, C = img_u8_hwc.shape
+    assert C == 3 and img_u8_hwc.dtype == torch.uint8 and img_u8_hwc.is_contiguous()
+    out = torch.empty(1, 3, H, W, dtype=torch.float32, device=img_u8_hwc.device)
+    L.check(L.load().ada_pre_image_nearest(_p(img_u8_hwc), H0, W0, _p(out), H, W, int(normalize), _stream()))
+    return out
+
+
+def mask_nearest(mask_u8, H=518, W=518):
+    """uint8 [H0,W0] (device, non-zero = inside) -> (mask01 [1,1,H,W], guide = mask01*2-1); infer.py:80-87,91,100-101."""
+    H0, W0 = mask_u8.shape
+    assert mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
+    m01 = torch.empty(1, 1, H, W, dtype=torch.float32, device=mask_u8.device)
+    guide = torch.empty_like(m01)
+    L.check(L.load().ada_pre_mask_nearest(_p(mask_u8), H0, W0, _p(m01), _p(guide), H, W, _stream()))
+    return m01, guide
+
+
+def minmax_normalize(depth):
+    """fp32 map -> (base01 = (d-min)/(max-min), observation = base01*2-1), same shape; infer.py:22,92."""
+    d = depth.contiguous()
+    base, obs = torch.empty_like(d), torch.empty_like(d)
+    scratch = torch.empty(2, dtype=torch.int32, device=d.device)
+    L.check(L.load().ada_post_minmax_normalize(_p(d), d.numel(), _p(base), _p(obs), _p(scratch), _stream()))
+    return base, obs
+
+
+def blend_seam(raw01, amodal, mask01):
+    """infer.py:30-44 median_filter_blend(amodal, raw, mask, 3) on [H,W] fp32 device maps."""
+    H, W = raw01.shape[-2:]
+    out = torch.empty(H, W, dtype=torch.float32, device=raw01.device)
+    L.check(L.load().ada_post_blend_seam(_p(raw01.contiguous()), _p(amodal.contiguous()), _p(mask01.contiguous()), _p(out), H, W,
+                                         _stream()))
+    return out

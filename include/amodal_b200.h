@@ -123,6 +123,24 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream);
 int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, const float* w, const float* b,
                      void* out_bf16, int32_t rows, int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x,
                      void* stream);
+/* ---- single-image pre/post-processing of the reference's infer.py on the device. All
+ * pointers are device pointers; one image; asynchronous on `stream`. Nearest sampling follows ATen
+ * (src = min(floor(dst * in/out), in-1)), which is what torchvision Resize(NEAREST) and F.interpolate's default use. */
+/* uint8 HWC image (cv2 channel order) -> fp32 [3,H,W] in [0,1]: rgb/255 then Resize(NEAREST) (infer.py:84-86);
+ * normalize != 0 also applies the ImageNet (x-mean)/std of infer.py:18 (input of the un-guided model). */
+int ada_pre_image_nearest(const uint8_t* img_hwc, int32_t H0, int32_t W0, float* out_chw, int32_t H, int32_t W,
+                          int32_t normalize, void* stream);
+/* uint8 mask (non-zero = inside, infer.py:80-81) -> nearest resize -> mask01 [H,W] in {0,1} (infer.py:87,100-101) and/or
+ * the network guide mask01*2-1 (infer.py:91). Either output may be NULL. */
+int ada_pre_mask_nearest(const uint8_t* mask, int32_t H0, int32_t W0, float* mask01, float* guide, int32_t H, int32_t W,
+                         void* stream);
+/* base01 = (d - min d) / (max d - min d) (infer.py:22) and/or observation = base01*2-1 (infer.py:92) over n values;
+ * scratch8 = 8 bytes of device memory. Either output may be NULL. */
+int ada_post_minmax_normalize(const float* depth, int64_t n, float* base01, float* obs, void* scratch8, void* stream);
+/* median_filter_blend(depth_amodal, depth_agg, mask, 3) of infer.py:30-44: out = mask ? amodal : raw, with the seam
+ * (3x3 zero-padded mask sum in (0,9)) replaced by the 3x3 box mean of the blended map (cv2.blur, BORDER_REFLECT_101). */
+int ada_post_blend_seam(const float* raw01, const float* amodal, const float* mask01, float* out, int32_t H, int32_t W,
+                        void* stream);
 /* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
 int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
 /* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */
