@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "postproc.cuh"
+#include "evalops.cuh"
 #include "gemm.cuh"
 #include "tma_host.h"
 
@@ -1473,6 +1474,25 @@ int ada_post_blend_seam(const float* raw01, const float* amodal, const float* ma
     ADA_REQUIRE(raw01 && amodal && mask01 && out && H > 1 && W > 1, "bad argument");
     ADA_REQUIRE(out != raw01 && out != amodal, "blend_seam is not in-place safe");
     blend_seam_kernel<<<(H * W + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(raw01, amodal, mask01, out, H, W);
+    ADA_CHECK_CUDA(cudaGetLastError());
+  });
+}
+
+// ---- per-sample evaluation post-ops of the validation loop
+int ada_eval_sample(const float* pred, int32_t h, int32_t w, const float* depth_gt, const float* depth_obs,
+                    const uint8_t* visible_mask, const uint8_t* object_mask, int32_t H, int32_t W, double* out24,
+                    double* scratch26, void* stream) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(pred && depth_gt && depth_obs && visible_mask && object_mask && out24 && scratch26, "bad argument");
+    ADA_REQUIRE(h > 0 && w > 0 && H > 0 && W > 0 && static_cast<long long>(H) * W < (1LL << 31), "bad size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EvalArgs a{pred, h, w, depth_gt, depth_obs, visible_mask, object_mask, H, W, scratch26, out24};
+    ADA_CHECK_CUDA(cudaMemsetAsync(scratch26, 0, sizeof(double) * kEvalScratch, st));
+    const int grid = static_cast<int>(std::min<long long>((static_cast<long long>(H) * W + 255) / 256, 148LL * 4));
+    eval_align_sums_kernel<<<grid, 256, 0, st>>>(a);
+    eval_metric_sums_kernel<<<grid, 256, 0, st>>>(a);
+    eval_finalize_kernel<<<1, 1, 0, st>>>(a);
     ADA_CHECK_CUDA(cudaGetLastError());
   });
 }

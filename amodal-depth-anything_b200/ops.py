@@ -166,3 +166,29 @@ def blend_seam(raw01, amodal, mask01):
     L.check(L.load().ada_post_blend_seam(_p(raw01.contiguous()), _p(amodal.contiguous()), _p(mask01.contiguous()), _p(out), H, W,
                                          _stream()))
     return out
+
+
+# ---- per-sample evaluation post-ops of the validation loop (include/amodal_b200.h, "row f3")
+EVAL_METRICS = ("abs_relative_difference", "squared_relative_difference", "rmse_linear", "rmse_log", "log10", "delta1_acc",
+                "delta2_acc", "delta3_acc", "i_rmse", "silog_rmse")  # config eval.eval_metrics order
+
+
+def eval_sample(pred, depth_gt, depth_obs, visible_mask, object_mask):
+    """pred [.., h, w] fp32 (network output), depth_gt / depth_obs [H, W] fp32, masks [H, W] bool/uint8, all on the device.
+    Returns a [24] float64 device tensor (layout in include/amodal_b200.h); no host synchronisation."""
+    h, w = pred.shape[-2:]
+    H, W = depth_gt.shape[-2:]
+    out = torch.empty(24, dtype=torch.float64, device=pred.device)
+    scratch = torch.empty(26, dtype=torch.float64, device=pred.device)
+    vis = visible_mask.to(torch.uint8).contiguous()
+    obj = object_mask.to(torch.uint8).contiguous()
+    L.check(L.load().ada_eval_sample(_p(pred.contiguous()), h, w, _p(depth_gt.contiguous()), _p(depth_obs.contiguous()), _p(vis),
+                                     _p(obj), H, W, _p(out), _p(scratch), _stream()))
+    return out
+
+
+def eval_sample_dict(out24):
+    """One host read of the 24 numbers -> {'scale', 'shift', 'pred': {metric: value}, 'aligned': {...}}."""
+    v = out24.cpu().tolist()
+    return {"scale": v[0], "shift": v[1], "pred": dict(zip(EVAL_METRICS, v[2:12])), "aligned": dict(zip(EVAL_METRICS, v[12:22])),
+            "n_visible": int(v[22]), "n_object": int(v[23])}

@@ -141,6 +141,16 @@ int ada_post_minmax_normalize(const float* depth, int64_t n, float* base01, floa
  * (3x3 zero-padded mask sum in (0,9)) replaced by the 3x3 box mean of the blended map (cv2.blur, BORDER_REFLECT_101). */
 int ada_post_blend_seam(const float* raw01, const float* amodal, const float* mask01, float* out, int32_t H, int32_t W,
                         void* stream);
+/* ---- per-sample evaluation post-ops of the validation loop on the device (SURVEY.md section 8 row f3;
+ * discriminative_trainer.py:542-613). pred [h,w] is resized to the ground-truth size (H,W) by nearest sampling (:542),
+ * aligned to depth_obs over visible_mask by least squares (src/util/alignment.py:7-54) and scored against depth_gt + 1e-5
+ * over object_mask with the ten metrics of src/util/metric.py:37-161, for the raw and the aligned prediction (:584-613).
+ * out24 (device doubles): [0] scale, [1] shift, [2..11] metrics of pred, [12..21] metrics of the aligned prediction in the
+ * order abs_relative_difference, squared_relative_difference, rmse_linear, rmse_log, log10, delta1_acc, delta2_acc,
+ * delta3_acc, i_rmse, silog_rmse; [22] visible pixels, [23] object pixels. scratch26: 26 device doubles. Masks: uint8. */
+int ada_eval_sample(const float* pred, int32_t h, int32_t w, const float* depth_gt, const float* depth_obs,
+                    const uint8_t* visible_mask, const uint8_t* object_mask, int32_t H, int32_t W, double* out24,
+                    double* scratch26, void* stream);
 /* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
 int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
 /* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */

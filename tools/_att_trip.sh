@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_infer_gpu.py -x -q -m gpu -s 2>&1 | tail -12
+RAW=vitg timeout 600 python tools/bench_pipeline.py 2>&1 | tail -2

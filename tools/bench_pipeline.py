@@ -14,6 +14,10 @@ raw = pkg.DepthAnythingV2(encoder=enc_raw, features=cfg["features"], out_channel
 am = pkg.AmodalDAv2(guide_type="mask+observation", encoder="vitl", pretrained=False).cuda().eval()
 with torch.no_grad():
     am.encoder.pretrained.patch_embed_guidance.proj.weight.normal_(std=0.02)
+    # random-init head: keep the un-guided output off the ReLU floor, otherwise min == max and the reference's min-max
+    # normalisation (infer.py:22) is 0/0
+    getattr(raw.depth_head.scratch.output_conv2, "2").bias.fill_(1.0)
+raw.repack()
 pipe = pkg.AmodalInference(raw, am)
 rng = np.random.default_rng(0)
 img = rng.integers(0, 256, size=(518, 518, 3), dtype=np.uint8)
