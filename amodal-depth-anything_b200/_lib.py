@@ -85,6 +85,7 @@ SIGNATURES = {
     "ada_launch_count": (c_int32, [c_void_p, c_int32, c_int32, c_int32]),
     "ada_read_intermediate": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64]),
     "ada_set_capture": (c_int32, [c_void_p, c_int32]),
+    "ada_set_graph": (c_int32, [c_void_p, c_int32]),
     "ada_set_profile": (c_int32, [c_void_p, c_int32]),
     "ada_profile_read": (c_int32, [c_void_p, c_int32, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                    POINTER(ctypes.c_double), POINTER(c_int32)]),

@@ -14,9 +14,9 @@ from . import ops
 
 
 class AmodalInference:
-    def __init__(self, model_raw, depth_amodal_model, size: int = 518):
-        self.model_raw = model_raw
-        self.model = depth_amodal_model
+    def __init__(self, model_raw, depth_amodal_model, size: int = 518, cuda_graph: bool = True):
+        self.model_raw = model_raw.set_graph(cuda_graph)      # one image per call is launch bound: replay as CUDA graphs
+        self.model = depth_amodal_model.set_graph(cuda_graph)
         self.size = size
         self.device = next(depth_amodal_model.parameters()).device
 

@@ -203,6 +203,8 @@ class _NativeModel(nn.Module):
         self._handle, self._handle_device, self._dirty = h, device, False
         if getattr(self, "_capture", False):
             lib.ada_set_capture(h, 1)
+        if getattr(self, "_graph", False):
+            lib.ada_set_graph(h, 1)
 
     def _run(self, x, guides):
         """x [B,3,H,W], guides: list of [B,c,H,W]; returns [B,1,H,W] fp32 on x's device, asynchronously on the current
@@ -241,6 +243,14 @@ class _NativeModel(nn.Module):
         self._capture = bool(on)
         if self._handle is not None:
             L.load().ada_set_capture(self._handle, int(on))
+
+    def set_graph(self, on: bool):
+        """Replay the forward as a CUDA graph (captured on the second call at a given input shape). For the launch-bound
+        small-batch case -- the reference's infer.py runs one image per call; results are identical to the eager path."""
+        self._graph = bool(on)
+        if self._handle is not None:
+            L.load().ada_set_graph(self._handle, int(on))
+        return self
 
     def read_intermediate(self, name: str, numel: int) -> torch.Tensor:
         out = torch.empty(numel, dtype=torch.float32, device=self._handle_device)

@@ -124,11 +124,19 @@ def run_reference(a):
 
 def workload_config(a, world):
     per_gpu = a.batch if a.scaling == "weak" else max(a.batch // world, 1)
+    in_mb = per_gpu * 5 * a.size * a.size * 4 / 1e6
+    # fp32 residual stream alone: tokens x D x 4 B, rewritten every block
+    d = {"vits": 384, "vitb": 768, "vitl": 1024, "vitg": 1536}[a.encoder]
+    x_mb = per_gpu * ((a.size // 14) ** 2 + 1) * d * 4 / 1e6
+    l2 = (f"per step {in_mb:.0f} MB of inputs and a {x_mb:.0f} MB fp32 token stream (plus GBs of bf16 activations) stream through "
+          f"the 126 MB L2" if in_mb + x_mb > 126 else
+          f"small-batch configuration: inputs ({in_mb:.0f} MB) and token stream ({x_mb:.0f} MB) fit the 126 MB L2 and are NOT "
+          f"flushed between steps -- latency figure, not the headline metric")
     return {"workload": f"AmodalDAv2 {a.encoder} {a.size}x{a.size} guide=mask+observation forward, batch {per_gpu}/GPU "
                         f"(BASELINE.json configs[2])",
             "encoder": a.encoder, "height": a.size, "width": a.size, "per_gpu_batch": per_gpu,
             "global_batch": per_gpu * world, "parallelism": f"image-sharded x{world}, weights replicated, no collective",
-            "l2": "inputs+activations per step exceed the 126 MB L2 (>=172 MB of inputs, GBs of activations at batch 32)"}
+            "cuda_graph": bool(getattr(a, "graph", False)), "l2": l2}
 
 
 def main():
@@ -142,6 +150,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak) / total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the forward as a CUDA graph (launch-bound small batches)")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--detail", default="", help="write per-launch-signature timings of the profile pass to this JSON file")
     a = ap.parse_args()
@@ -174,6 +183,8 @@ def main():
         model.encoder.pretrained.patch_embed_guidance.proj.weight.normal_(std=0.02)
         model.encoder.pretrained.patch_embed_guidance.proj.bias.uniform_(-0.05, 0.05)
     model = model.to(dev).eval()
+    if a.graph:
+        model.set_graph(True)
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.rand(B, 3, H, W, device=dev, generator=g)

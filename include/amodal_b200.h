@@ -73,6 +73,11 @@ int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W);
  * "path_1".."path_4" (NHWC), "tokens" (x after prepare_tokens_with_masks; needs ada_set_capture(h,1)). */
 int ada_read_intermediate(ada_handle h, const char* name, float* dst, int64_t count);
 int ada_set_capture(ada_handle h, int32_t on);
+/* Launch-bound small batches (the reference's infer.py runs one image at a time): when on, the second ada_forward at a
+ * given (B,H,W) captures the whole forward into a CUDA graph over handle-owned staging copies of the inputs / output and
+ * later calls replay it (3-5 small device copies + one graph launch instead of 136-332 kernel launches). Results are
+ * bit-identical to the eager path. Off by default; ignored while profiling / capturing intermediates. */
+int ada_set_graph(ada_handle h, int32_t on);
 /* Measurement hook (bench.py): when on, every kernel launch of ada_forward is bracketed by CUDA events on the launch
  * stream. ada_profile_read syncs, then sums per kernel class since the last read: elapsed ms, algorithmic FLOPs,
  * algorithmic bytes, launches. Classes: 0 tcgen05 GEMM (linear), 1 tcgen05 GEMM (implicit conv3x3), 2 attention,

@@ -18,7 +18,7 @@ with torch.no_grad():
     # normalisation (infer.py:22) is 0/0
     getattr(raw.depth_head.scratch.output_conv2, "2").bias.fill_(1.0)
 raw.repack()
-pipe = pkg.AmodalInference(raw, am)
+pipe = pkg.AmodalInference(raw, am, cuda_graph=bool(int(os.environ.get('GRAPH', '1'))))
 rng = np.random.default_rng(0)
 img = rng.integers(0, 256, size=(518, 518, 3), dtype=np.uint8)
 mask = np.zeros((518, 518), np.uint8); mask[100:400, 150:420] = 255
@@ -33,5 +33,5 @@ for _ in range(n):
     agg = out["depth_agg"].cpu()      # the caller's read of the result, as infer.py:105 does
 e1.record(); torch.cuda.synchronize(); t1 = time.perf_counter()
 assert torch.isfinite(agg).all()
-print(json.dumps({"pipeline": f"{enc_raw} un-guided + vitl guided, 518x518, 1 image", "ms_per_image_device": e0.elapsed_time(e1) / n,
+print(json.dumps({"cuda_graph": os.environ.get("GRAPH", "1"), "pipeline": f"{enc_raw} un-guided + vitl guided, 518x518, 1 image", "ms_per_image_device": e0.elapsed_time(e1) / n,
                   "ms_per_image_wall": (t1 - t0) / n * 1e3, "launches_raw": raw.launch_count(), "launches_amodal": am.launch_count()}))
