@@ -426,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int passes = g.has_relu_copy ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
               const uint32_t buf = buf0 + static_cast<uint32_t>(sbuf) * 4096u;
-              if (lane == 0) bulk_wait_read<Cfg::kStgBufs - 1>();  // the store that last used this buffer has drained it
+              bulk_wait_read_w<Cfg::kStgBufs - 1>();  // (elected lane) the store that last used this buffer has drained it
               __syncwarp();
               stamp(4);
               if (pass == 1) {
@@ -445,13 +445,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               fence_proxy_async_smem();
               __syncwarp();
               stamp(5);
-              if (lane == 0) {
+              {  // whole warp converged, elected lane issues store + commit (no uniform-register waterfall)
                 const CUtensorMap* tm = (pass == 0) ? &tmap_c : &tmap_c2;
                 if (g.a_mode == A_CONV3X3)
-                  tma_store_4d(tm, buf, oc, x0, y0 + 2 * q, img);
+                  tma_store_4d_commit_w(tm, buf, oc, x0, y0 + 2 * q, img);
                 else
-                  tma_store_2d(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
-                bulk_commit();
+                  tma_store_2d_commit_w(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
               }
               if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
             }
@@ -538,7 +537,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (lane == 0) bulk_wait<0>();  // all TMA stores of this warp have completed before the CTA retires
+    bulk_wait_w<0>();  // (same elected lane) all TMA stores of this warp have completed before the CTA retires
     __syncwarp();
   }
 

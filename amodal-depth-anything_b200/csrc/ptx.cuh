@@ -134,6 +134,33 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() {  // <= N groups not yet complete (writes performed)
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Whole-warp (elected lane) TMA store + commit and the matching read-wait: bulk async-groups are per thread, and
+// elect.sync with a full member mask always picks the same lane, so store/commit/wait stay on one thread.
+__device__ __forceinline__ void tma_store_2d_commit_w(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@e cp.async.bulk.commit_group;\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_commit_w(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t"
+      "@e cp.async.bulk.commit_group;\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_w() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_w() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.wait_group %0;\n\t}" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
