@@ -346,9 +346,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
-  uint32_t box[3] = {64, 128, 1}, box_kv[3] = {64, static_cast<uint32_t>(kAttKV), 1};
+  uint32_t box[3] = {64, 128, 1};  // Q tile and K/V tiles: 128 tokens x 64 head dims
+  static_assert(kAttQ == 128 && kAttKV == 128, "the attention tensor map assumes 128-token tiles");
   CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, str, box);
-  CUtensorMap tmkv = make_tmap_bf16(qkv, 3, dims, str, box_kv);
   uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t ostr[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
   CUtensorMap tmo = make_tmap_bf16(out, 3, odims, ostr, box);
@@ -360,7 +360,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-#define ADA_ATT_LAUNCH(V, SMEM) attention_tcgen05_kernel<V><<<grid, kAttThreads, SMEM, st>>>(tm, tmkv, tmo, a)
+#define ADA_ATT_LAUNCH(V, SMEM) attention_tcgen05_kernel<V><<<grid, kAttThreads, SMEM, st>>>(tm, tmo, a)
   switch (variant) {
     case 1: ADA_ATT_LAUNCH(1, kAttSmemBytes); break;
     case 2: ADA_ATT_LAUNCH(2, kAttSmemBytes); break;

@@ -46,8 +46,7 @@ struct AttArgs {
 // replaced by a copy (timing skeleton only, wrong results), 3/4/5 = other FMA-pipe fractions, 10 = clock64 timeline.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap /*tmap_kv*/,
-                         const __grid_constant__ CUtensorMap tmap_out,
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                          const AttArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const uint32_t sbase = smem_u32(att_smem);
@@ -96,33 +95,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &tmap_qkv, q_full, head * kAttD, q0, img);
-    }
+    // ------------------------------------------------------------------ producer (whole warp, elected lane per instruction)
+    mbar_expect_tx_w(q_full, 16384);
+    tma_load_3d_w(sQ, &tmap_qkv, q_full, head * kAttD, q0, img);
     for (int j = 0; j < num_kv; ++j) {
       const int s = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(k_empty(s), ph ^ 1u, 0x500 + s);
-      if (lane == 0) {
-        if (VARIANT == 9 && j >= 2) {
-          mbar_arrive(k_full(s));  // measurement: reuse the resident tile, no L2 -> SM traffic
-        } else {
-          mbar_expect_tx(k_full(s), 16384);
-          tma_load_3d(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
-        }
-      }
+      mbar_expect_tx_w(k_full(s), 16384);
+      tma_load_3d_w(sK + s * 16384, &tmap_qkv, k_full(s), a.D + head * kAttD, j * kAttKV, img);
       mbar_wait(v_empty(s), ph ^ 1u, 0x510 + s);
-      if (lane == 0) {
-        if (VARIANT == 9 && j >= 2) {
-          mbar_arrive(v_full(s));
-        } else {
-          mbar_expect_tx(v_full(s), 16384);
-          tma_load_3d(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
-        }
-      }
-      __syncwarp();
+      mbar_expect_tx_w(v_full(s), 16384);
+      tma_load_3d_w(sV + s * 16384, &tmap_qkv, v_full(s), 2 * a.D + head * kAttD, j * kAttKV, img);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -251,7 +235,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(h ? s1[i] : s0[i]), __uint_as_float(h ? s1[i + 1] : s0[i + 1])),
                                      c2, nmc2);
           float p0, p1;
-          if constexpr (VARIANT == 2 || VARIANT == 9) {
+          if constexpr (VARIANT == 2) {
             f2_unpack(x2, p0, p1);
           } else {
             if ((kEmuMask >> (i >> 1)) & 1u) {

@@ -12,20 +12,19 @@ for _ in range(3):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ops.attention(qkv, B, N, H); e1.record(); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 256)()
-L.check(L.load().ada_debug_timeline(buf, 256))
+buf = (ctypes.c_longlong * 512)()
+L.check(L.load().ada_debug_timeline(buf, 512))
 t = list(buf)
 print("kernel ms", e0.elapsed_time(e1), "pad", os.environ.get("ADA_ATT_PAD", "0"))
 names = ["loop_top", "s_full", "ldtm", "max+xchg", "exps", "o_full", "sttm"]
 base = t[0]
+print("softmax thread 64 (one of the two owners of a row), cycles per phase and 128-key tile")
 for j in range(11):
     r = t[j * 8:j * 8 + 7]
     d = [r[0] - base] + [r[k] - r[k - 1] for k in range(1, 7)]
     print(f"tile {j:2d}: start {d[0]:7d}  " + "  ".join(f"{names[k]}+{d[k]:5d}" for k in range(1, 7)))
-inames = ["top", "s_free", "S issued", "p_full", "PV issued"]
+inames = ["top", "s_free", "S(j+1) issued", "p_full", "PV(j) issued"]
+print("issuer thread, absolute cycles")
 for j in range(11):
     r = t[128 + j * 8:128 + j * 8 + 5]
     print(f"issuer {j:2d}: " + "  ".join(f"{inames[k]}@{r[k] - base:6d}" for k in range(5) if r[k]))
-for j in range(11):
-    r = t[j * 8:j * 8 + 7]
-    print(f"softmx {j:2d}: " + "  ".join(f"{names[k]}@{r[k] - base:6d}" for k in range(7)))
