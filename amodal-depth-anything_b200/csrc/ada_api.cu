@@ -276,8 +276,15 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     prof.r->tag = g.epi | (g.act << 4) | (bn << 8) | (cg << 20);
   }
   // one instantiation per (tile, pairing, epilogue): keeps each kernel's code small (instruction-cache resident)
+  // EPI_BF16 is specialised at compile time on (activation, residual adds); the rest of the launcher keeps seeing EPI_BF16
+  int epi_t = g.epi;
+  if (g.epi == EPI_BF16) {
+    const bool resid = g.resid1 != nullptr || g.resid2 != nullptr;
+    ADA_REQUIRE(!(resid && g.act == ACT_GELU), "EPI_BF16: GELU and residual adds are not combined on this path");
+    epi_t = resid ? EPI_BF16_RESID : (g.act == ACT_GELU) ? EPI_BF16_GELU : (g.act == ACT_RELU) ? EPI_BF16_RELU : EPI_BF16;
+  }
 #define ADA_GEMM_CASE(BN_, CG_, EPI_)                                      \
-  if (bn == BN_ && cg == CG_ && g.epi == EPI_) {                           \
+  if (bn == BN_ && cg == CG_ && epi_t == EPI_) {                           \
     launch_gemm_bn<BN_, CG_, EPI_>(ta, tb, tc, tc2, g, num_tiles, st);     \
     launched = true;                                                       \
   }
@@ -287,6 +294,21 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_GEMM_CASE(128, 2, EPI_BF16)
   ADA_GEMM_CASE(256, 1, EPI_BF16)
   ADA_GEMM_CASE(256, 2, EPI_BF16)
+  ADA_GEMM_CASE(64, 1, EPI_BF16_GELU)
+  ADA_GEMM_CASE(128, 1, EPI_BF16_GELU)
+  ADA_GEMM_CASE(128, 2, EPI_BF16_GELU)
+  ADA_GEMM_CASE(256, 1, EPI_BF16_GELU)
+  ADA_GEMM_CASE(256, 2, EPI_BF16_GELU)
+  ADA_GEMM_CASE(64, 1, EPI_BF16_RELU)
+  ADA_GEMM_CASE(128, 1, EPI_BF16_RELU)
+  ADA_GEMM_CASE(128, 2, EPI_BF16_RELU)
+  ADA_GEMM_CASE(256, 1, EPI_BF16_RELU)
+  ADA_GEMM_CASE(256, 2, EPI_BF16_RELU)
+  ADA_GEMM_CASE(64, 1, EPI_BF16_RESID)
+  ADA_GEMM_CASE(128, 1, EPI_BF16_RESID)
+  ADA_GEMM_CASE(128, 2, EPI_BF16_RESID)
+  ADA_GEMM_CASE(256, 1, EPI_BF16_RESID)
+  ADA_GEMM_CASE(256, 2, EPI_BF16_RESID)
   ADA_GEMM_CASE(128, 1, EPI_SWIGLU)
   ADA_GEMM_CASE(256, 1, EPI_SWIGLU)
   ADA_GEMM_CASE(256, 2, EPI_SWIGLU)

@@ -46,8 +46,17 @@ enum EpiMode : int {
   EPI_EMBED = 2,      // out_f32[b*(P+1)+1+p, :] = acc + aux[p, :]           (patch embed: + bias + pos-embed, skip cls row)
   EPI_CONVT = 3,      // k == s transposed conv: pixel-shuffle scatter, + bias[co]
   EPI_TAIL = 4,       // sigmoid(relu(acc + bias) . aux[0:32] + aux[32]) -> fp32 per pixel (BN must be 32)
-  EPI_SWIGLU = 5      // columns interleaved in 32-wide (x1, x2) chunk pairs: out = silu(x1 + b1) * (x2 + b2); TMA store
+  EPI_SWIGLU = 5,     // columns interleaved in 32-wide (x1, x2) chunk pairs: out = silu(x1 + b1) * (x2 + b2); TMA store
+  // compile-time specialisations of EPI_BF16, picked by the launcher from (act, residuals): with those as run-time
+  // switches inside the unrolled epilogue loop the compiler emitted ~130 instructions per 8 outputs (register shuffles to
+  // merge the paths, ~40 predicated-off residual instructions) instead of ~20.
+  EPI_BF16_GELU = 6,
+  EPI_BF16_RELU = 7,
+  EPI_BF16_RESID = 8
 };
+__host__ __device__ constexpr bool epi_is_bf16(int e) {
+  return e == EPI_BF16 || e == EPI_BF16_GELU || e == EPI_BF16_RELU || e == EPI_BF16_RESID;
+}
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1 };
 
@@ -292,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t st_sw = static_cast<uint32_t>(lane & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr bool tma_out = (EPI == EPI_BF16 || EPI == EPI_SWIGLU);
+    constexpr bool tma_out = (epi_is_bf16(EPI) || EPI == EPI_SWIGLU);
     const bool tl = g.debug_timeline && blockIdx.x == 0 && warp == 4 && lane == 0;
     int tl_i = 0;
     auto stamp = [&](int k) {
@@ -338,7 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int n = n0 + i;
           const float bv = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
           const float gv = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
-          s_bias[i] = (EPI == EPI_BF16) ? bv * gv : bv;  // EPI_BF16 applies (acc + b) * gamma as fma(acc, gamma, b * gamma)
+          s_bias[i] = epi_is_bf16(EPI) ? bv * gv : bv;  // EPI_BF16* apply (acc + b) * gamma as fma(acc, gamma, b * gamma)
           s_gamma[i] = gv;
         }
         named_bar_sync(1, kEpiThreads);
@@ -388,27 +397,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float* gg = s_gamma + cg * 64 + h * 32;
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
-                  // (acc + bias) * gamma as one packed FMA per pair: the staged bias is already multiplied by gamma
+                  // (acc + bias) * gamma as one packed FMA per pair: the staged bias is already multiplied by gamma and
+                  // the staged gamma is 1 when there is none (no run-time switch inside the unrolled loop)
                   uint64_t v2[4];
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const uint64_t a2 = f2_pack(__uint_as_float(r[gi * 8 + 2 * j]), __uint_as_float(r[gi * 8 + 2 * j + 1]));
-                    const uint64_t b2 = *reinterpret_cast<const uint64_t*>(bb + gi * 8 + 2 * j);
-                    v2[j] = (g.gamma != nullptr) ? f2_fma(a2, *reinterpret_cast<const uint64_t*>(gg + gi * 8 + 2 * j), b2)
-                                                 : f2_add(a2, b2);
+                    v2[j] = f2_fma(a2, *reinterpret_cast<const uint64_t*>(gg + gi * 8 + 2 * j),
+                                   *reinterpret_cast<const uint64_t*>(bb + gi * 8 + 2 * j));
                   }
-                  if (g.act == ACT_GELU) {
+                  if constexpr (EPI == EPI_BF16_GELU) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v2[j] = gelu_erf2(v2[j]);
                   }
                   float v[8];
 #pragma unroll
                   for (int j = 0; j < 4; ++j) f2_unpack(v2[j], v[2 * j], v[2 * j + 1]);
-                  if (g.act == ACT_RELU) {
+                  if constexpr (EPI == EPI_BF16_RELU) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
                   }
-                  if (g.resid1 != nullptr || g.resid2 != nullptr) {
+                  if constexpr (EPI == EPI_BF16_RESID) {
+                    if (g.act == ACT_RELU) {  // (only the operator-level ABI combines ReLU with residual adds)
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
                     const int n = oc + h * 32 + gi * 8;
                     if (valid && n < g.N) {
                       const long long off = orow * g.ldo + n;
