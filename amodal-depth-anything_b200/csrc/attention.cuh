@@ -44,6 +44,11 @@ struct AttArgs {
 
 // VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = every exponential on MUFU, 2 = exponentials
 // replaced by a copy (timing skeleton only, wrong results), 3/4/5 = other FMA-pipe fractions, 10 = clock64 timeline.
+template <bool B>
+struct IntTag {
+  static constexpr bool value = B;
+};
+
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
@@ -163,7 +168,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     auto stamp = [&](int j, int k) {
       if (tl) g_dev_timeline[j * 8 + k] = clock64();
     };
-    for (int j = 0; j < num_kv; ++j) {
+    // One KV tile. MASKED is a compile-time tag: only the ragged last tile carries the 64 compare+select pairs that
+    // overwrite the scores of keys past N (zero-filled by TMA) with -inf. As a run-time `if` inside a single loop body the
+    // compiler if-converted them into ~130 always-executed instructions per tile (of ~450).
+    auto tile = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       const int kv_valid = min(kAttKV, a.N - j * kAttKV) - half * 64;  // valid keys inside this thread's 64 columns
       stamp(j, 0);
       mbar_wait(s_full, j & 1, 0x560);
@@ -179,7 +188,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       // hand off in tens of cycles; the mbarrier round trip they replace cost ~350 cycles per hop and made the kernel
       // synchronisation-latency bound (skeleton 0.23 ms of 0.39 ms with all math removed).
       if (j + 1 < num_kv) named_bar_arrive(6, kAttSoftmaxThreads + 32);
-      if (kv_valid < 64) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
+      if constexpr (MASKED) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= kv_valid) s0[i] = 0xff800000u;
@@ -280,7 +289,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       stamp(j, 6);
       tc_fence_before();
       named_bar_arrive(7, kAttSoftmaxThreads + 32);
-    }
+    };
+    const bool ragged = (a.N % kAttKV) != 0;
+#pragma unroll 1
+    for (int j = 0; j < num_kv - 1; ++j) tile(j, IntTag<false>{});
+    if (ragged)
+      tile(num_kv - 1, IntTag<true>{});
+    else
+      tile(num_kv - 1, IntTag<false>{});
     // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile is dead once the last S MMA has retired) -> one TMA
     //      store per CTA (row-per-thread global stores touch 32 cache lines per warp instruction).
     float* xl = xch + 512;
