@@ -1,3 +1,8 @@
-timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k attention 2>&1 | tail -3
-for v in 0 1 3 2; do ADA_ATT_VARIANT=$v timeout 60 python tools/bench_attention.py 2>&1 | tail -1; done
-ADA_ATT_VARIANT=0 N=5477 B=4 timeout 60 python tools/bench_attention.py 2>&1 | tail -1
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('metric','value','unit','n_gpus','steps','warmup','ms_per_step','scaling','vs_baseline','dtype','gpu_launches')})
+print('e2e', d['e2e']); print('roofline', d['roofline']); print('cpu', d['cpu_baseline']); print('clocks', d['clocks'])
+PY
