@@ -98,7 +98,7 @@ static int env_int(const char* name, int dflt) {
 template <int BN, int CG, int EPI>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                            const GemmArgs& g, int num_tiles, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -264,6 +264,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
       g.has_relu_copy = 1;
     }
   }
+  if (g.epi == EPI_RESID_F32) {
+    ADA_REQUIRE(L.a_mode == A_LINEAR && g.out_f32 != nullptr && g.ldo % 4 == 0, "RESID_F32: linear A, fp32 in/out, ldo % 4");
+    tc = make_tmap_f32_2d(g.out_f32, static_cast<uint64_t>(L.N), static_cast<uint64_t>(L.M), static_cast<uint64_t>(g.ldo), 32, 32);
+  }
   const int tiles_n = (L.N + bn - 1) / bn;
   const int num_tiles = tiles_m * tiles_n;
   const double kreal = (L.a_mode == A_CONV3X3) ? 9.0 * L.Cin : static_cast<double>(L.K);
@@ -309,6 +313,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_GEMM_CASE(128, 2, EPI_BF16_RESID)
   ADA_GEMM_CASE(256, 1, EPI_BF16_RESID)
   ADA_GEMM_CASE(256, 2, EPI_BF16_RESID)
+  ADA_GEMM_CASE(64, 1, EPI_RESID_F32)
+  ADA_GEMM_CASE(128, 1, EPI_RESID_F32)
+  ADA_GEMM_CASE(256, 1, EPI_RESID_F32)
+  ADA_GEMM_CASE(256, 2, EPI_RESID_F32)
   ADA_GEMM_CASE(128, 1, EPI_SWIGLU)
   ADA_GEMM_CASE(256, 1, EPI_SWIGLU)
   ADA_GEMM_CASE(256, 2, EPI_SWIGLU)
@@ -1048,14 +1056,13 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     ADA_CHECK_CUDA(cudaMemcpyAsync(m->tokens_dbg, m->x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, st));
 
   // ---- encoder blocks (block.py:82-107 eval branch). The fp32 stream x is only touched by the LayerNorm kernel:
-  //      the attention branch leaves gamma1 * (W h + b) in `ybuf` and the MLP branch gamma2 * (...) in `ybuf2` (bf16).
-  //      norm2 normalises x + ybuf without storing it; the NEXT block's norm1 (or the tap norm) adds both and norm1
-  //      stores x <- (x + ybuf) + ybuf2 (block.py:105-106): one fp32 write of the stream per block.
+  //      the fp32 residual stream x is updated in place by the proj / fc2 GEMM epilogues (EPI_RESID_F32: the x tile
+  //      travels through TMA-staged shared memory, coalesced and under the GEMM's tensor time); the LayerNorm kernels only
+  //      read x and write the bf16 normalised activations (6 bytes per element).
   int tap_i = 0;
-  const __nv_bfloat16 *pend1 = nullptr, *pend2 = nullptr;  // residual-branch outputs not yet added to x
   for (int i = 0; i < c.depth; ++i) {
     const BlockW& w = m->blocks[i];
-    launch_layernorm(m->x, pend1, pend2, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 1, st);
+    launch_layernorm(m->x, nullptr, nullptr, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 0, st);
     {
       GemmArgs e{};
       e.epi = EPI_BF16;
@@ -1067,14 +1074,14 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     launch_attention(m->qkv, m->att, B, N, heads, st);
     {
       GemmArgs e{};
-      e.epi = EPI_BF16;
+      e.epi = EPI_RESID_F32;  // x += gamma1 * (att W^T + b), in place through TMA (block.py:105)
       e.bias = w.bproj;
       e.gamma = w.g1;
-      e.out_bf16 = m->ybuf;
+      e.out_f32 = m->x;
       e.ldo = D;
       linear(m->att, M, D, D, w.wproj, D, D, e, st);
     }
-    launch_layernorm(m->x, m->ybuf, nullptr, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 0, st);
+    launch_layernorm(m->x, nullptr, nullptr, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 0, st);
     const int Hd = c.ffn_hidden;
     {
       GemmArgs e{};
@@ -1092,19 +1099,16 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     }
     {
       GemmArgs e{};
-      e.epi = EPI_BF16;
+      e.epi = EPI_RESID_F32;  // x += gamma2 * (h W^T + b) (block.py:106)
       e.bias = w.b2;
       e.gamma = w.g2;
-      e.out_bf16 = m->ybuf2;
+      e.out_f32 = m->x;
       e.ldo = D;
       linear(m->hbuf, M, Hd, Hd, w.w2, D, Hd, e, st);
     }
-    pend1 = m->ybuf;
-    pend2 = m->ybuf2;
     if (tap_i < 4 && i == c.taps[tap_i]) {
-      // shared final norm of (x + both branches), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is updated
-      // by the next block's first LayerNorm, so nothing is written back here
-      launch_layernorm(m->x, pend1, pend2, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
+      // shared final norm, cls dropped, NHWC patch map (dinov2.py:337-340)
+      launch_layernorm(m->x, nullptr, nullptr, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
       ++tap_i;
     }
   }

@@ -52,7 +52,12 @@ enum EpiMode : int {
   // merge the paths, ~40 predicated-off residual instructions) instead of ~20.
   EPI_BF16_GELU = 6,
   EPI_BF16_RELU = 7,
-  EPI_BF16_RESID = 8
+  EPI_BF16_RESID = 8,
+  // fp32 in-place residual update through TMA: out_f32[m, n] += (acc + bias) * gamma. The x tile is fetched into the
+  // warp's swizzled staging buffer by TMA (prefetched one 32-column block ahead), updated in shared memory and stored back
+  // by TMA, so the fp32 residual stream of the encoder (block.py:105-106) is read and written coalesced, under the GEMM's
+  // tensor time, instead of by the LayerNorm kernel (which drops from 14 / 8 to 6 bytes per element).
+  EPI_RESID_F32 = 9
 };
 __host__ __device__ constexpr bool epi_is_bf16(int e) {
   return e == EPI_BF16 || e == EPI_BF16_GELU || e == EPI_BF16_RELU || e == EPI_BF16_RESID;
@@ -82,7 +87,7 @@ struct GemmArgs {
   int debug_timeline;       // bring-up: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase into g_dev_timeline
 };
 
-template <int BN, int CG>
+template <int BN, int CG, int EPI = 0>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBRows = BN / CG;                         // B rows (N) loaded by one CTA
@@ -91,14 +96,14 @@ struct GemmCfg {
   // epilogue staging: one 4 KB buffer per epilogue warp for the 256-wide tiles (two 64-column groups per warp and a long
   // main loop hide the TMA-store drain), two for narrower tiles (small-K, store-bound GEMMs: a single buffer made every
   // tile wait ~1 us for the previous store to release it)
-  static constexpr int kStgBufs = (BN == 256) ? 1 : 2;
-  static constexpr int kStagesFit = (232448 - 8 * kStgBufs * 4096 - 2 * 256 * 4 - 256) / kStageBytes;
+  static constexpr int kStgBufs = (EPI == EPI_RESID_F32) ? 3 : (BN == 256) ? 1 : 2;  // RESID_F32: load-ahead + store-behind
+  static constexpr int kStagesFit = (232448 - 8 * kStgBufs * 4096 - 2 * 256 * 4 - 512) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (BN * 2 < 32) ? 32 : BN * 2;  // 2 accumulator stages, power of two >= 32
   static constexpr int kStagingBytes = 8 * kStgBufs * 4096;      // 8 epilogue warps x kStgBufs x (32 rows x 128 B)
   static constexpr int kVecBytes = 2 * 256 * 4;                  // bias + gamma of the current N tile
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;
   // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1 KB aligned (checked)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     const GemmArgs g) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EPI>;
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -155,6 +160,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 4);
+  // EPI_RESID_F32: one load barrier per epilogue warp and staging buffer
+  auto xld_bar = [&](int w, int b) { return bar_base + 8u * (2 * Cfg::kStages + 6 + w * 3 + b); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,6 +174,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), CG);   // one arrive.expect_tx per producing CTA (leader's barrier is the one used)
       mbar_init(empty_bar(s), 1);   // tcgen05.commit (multicast to both CTAs when CG == 2)
+    }
+    if constexpr (EPI == EPI_RESID_F32) {
+      for (int w = 0; w < 8; ++w)
+        for (int b = 0; b < 3; ++b) mbar_init(xld_bar(w, b), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -302,6 +313,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr bool tma_out = (epi_is_bf16(EPI) || EPI == EPI_SWIGLU);
+    constexpr bool stage_vec = tma_out || EPI == EPI_RESID_F32;  // bias / gamma staged in shared memory per N tile
+    uint32_t xld_phase = 0;  // EPI_RESID_F32: phase bit per staging buffer (bits 0..2)
+    int xbuf = 0;            // EPI_RESID_F32: staging buffer of the next block to consume
     const bool tl = g.debug_timeline && blockIdx.x == 0 && warp == 4 && lane == 0;
     int tl_i = 0;
     auto stamp = [&](int k) {
@@ -341,13 +355,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float* s_bias = s_vec;
       float* s_gamma = s_bias + 256;
       // (no bias and no gamma: the vectors are tile-invariant -- staged once for the first tile, then no barriers)
-      if (tma_out && (g.bias != nullptr || g.gamma != nullptr || t == unit)) {  // tma_out is constexpr
+      if (stage_vec && (g.bias != nullptr || g.gamma != nullptr || t == unit)) {  // stage_vec is constexpr
         named_bar_sync(1, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;
           const float bv = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.0f;
           const float gv = (g.gamma != nullptr && n < g.N) ? __ldg(g.gamma + n) : 1.0f;
-          s_bias[i] = epi_is_bf16(EPI) ? bv * gv : bv;  // EPI_BF16* apply (acc + b) * gamma as fma(acc, gamma, b * gamma)
+          s_bias[i] = (epi_is_bf16(EPI) || EPI == EPI_RESID_F32) ? bv * gv : bv;  // (acc + b) * gamma as fma(acc, gamma, b * gamma)
           s_gamma[i] = gv;
         }
         named_bar_sync(1, kEpiThreads);
@@ -473,6 +487,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
               if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
             }
+          }
+        }
+      } else if constexpr (EPI == EPI_RESID_F32) {
+        if constexpr (BN >= 64) {
+          // This warp's blocks of the tile: 32 rows x 32 fp32 columns each (one 4 KB staging buffer, 128-byte rows),
+          // column groups cg = half, half + 2, ... of 64 columns, two blocks per group.
+          const int ew = warp - 4;
+          const int row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32;
+          int nblk = 0;
+          for (int cg = half; cg < BN / 64; cg += 2)
+            if (n0 + cg * 64 < g.N) nblk += 2;
+          auto blk_col = [&](int k) { return n0 + (half + 2 * (k >> 1)) * 64 + (k & 1) * 32; };
+          auto fetch = [&](int k, int b) {  // x block k -> staging buffer b (whole warp, elected lane)
+            mbar_expect_tx_w(xld_bar(ew, b), 4096);
+            tma_load_2d_w(buf0 + static_cast<uint32_t>(b) * 4096u, &tmap_c, xld_bar(ew, b), blk_col(k), row0);
+          };
+          // the first block is fetched before the accumulator is complete: the read of x overlaps the main loop's tail
+          if (nblk > 0) {
+            bulk_wait_read_w<1>();  // at most one earlier store may still be reading shared memory (another buffer)
+            __syncwarp();
+            fetch(0, xbuf);
+          }
+          // (the mbar_wait on tfull above already happened: accumulators are ready)
+#pragma unroll 1
+          for (int k = 0; k < nblk; ++k) {
+            const int b = xbuf;
+            const int bn_ = (b == 2) ? 0 : b + 1;
+            if (k + 1 < nblk) {  // prefetch the next block; its buffer was last read by the store issued two blocks ago
+              bulk_wait_read_w<1>();
+              __syncwarp();
+              fetch(k + 1, bn_);
+            }
+            const int c_local = (half + 2 * (k >> 1)) * 64 + (k & 1) * 32;  // first accumulator column of this block
+            uint32_t r[32];
+            tmem_ld32(t_addr + c_local, r);
+            tmem_ld_wait();
+            mbar_wait(xld_bar(ew, b), (xld_phase >> b) & 1u, 0x480 + b);
+            xld_phase ^= 1u << b;
+            const uint32_t buf = buf0 + static_cast<uint32_t>(b) * 4096u;
+            const float* bb = s_bias + c_local;
+            const float* gg = s_gamma + c_local;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {  // 4 fp32 per 16-byte chunk, chunk index XOR (row & 7) = the 128-byte swizzle
+              const uint32_t addr = buf + st_row + ((static_cast<uint32_t>(c) ^ st_sw) << 4);
+              uint64_t x01, x23;
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x01), "=l"(x23) : "r"(addr));
+              const uint64_t v01 = f2_fma(f2_pack(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1])),
+                                          *reinterpret_cast<const uint64_t*>(gg + 4 * c), *reinterpret_cast<const uint64_t*>(bb + 4 * c));
+              const uint64_t v23 = f2_fma(f2_pack(__uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])),
+                                          *reinterpret_cast<const uint64_t*>(gg + 4 * c + 2),
+                                          *reinterpret_cast<const uint64_t*>(bb + 4 * c + 2));
+              x01 = f2_add(x01, v01);
+              x23 = f2_add(x23, v23);
+              asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(x01), "l"(x23) : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            tma_store_2d_commit_w(&tmap_c, buf, blk_col(k), row0);  // clips rows >= M and columns >= N
+            xbuf = bn_;
           }
         }
       } else if constexpr (EPI == EPI_TAIL) {

@@ -64,4 +64,19 @@ inline CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t rows,
   return make_tmap_bf16(base, 2, dims, str, box);
 }
 
+// fp32 row-major [rows, inner] map with 32 x 32 boxes (128-byte rows, 128-byte swizzle): the in-place residual epilogue
+inline CUtensorMap make_tmap_f32_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint32_t box_inner,
+                                    uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstr[1] = {pitch_elems * 4};
+  cuuint32_t bx[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, bx, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (fp32) failed: code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
 }  // namespace ada

@@ -106,7 +106,8 @@ typedef struct ada_gemm_desc {
   const void* Bw;       /* bf16 [N,K] row-major (ldb): the torch Linear / packed conv weight */
   int32_t M, N, K, lda, ldb;
   int32_t a_mode;       /* 0 linear, 1 conv3x3 (pad 1, stride 1) */
-  int32_t epi, act;     /* see EpiMode / ActMode in csrc/gemm.cuh */
+  int32_t epi, act;     /* see EpiMode / ActMode in csrc/gemm.cuh (0 bf16 out, 2 embed, 3 convT, 4 tail, 5 SwiGLU,
+                           9 fp32 in-place residual: out_f32 += (acc + bias) * gamma) */
   int32_t batch, H, W, Cin;   /* conv mode geometry; EPI_CONVT: input grid */
   const float* bias;
   const float* gamma;

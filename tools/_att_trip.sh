@@ -1,8 +1,9 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.err; python - <<'PY'
+for c in gemm_resid_f32_small gemm_resid_f32_ragged gemm_resid_f32 gemm_resid_f32_cg2; do timeout 120 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "$c" 2>&1 | tail -3; done
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python bench.py --no-cpu-baseline --detail gpurun_out/detail.json 2>&1 | tail -1 > gpurun_out/bench_w.json; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('metric','value','unit','n_gpus','steps','warmup','ms_per_step','scaling','vs_baseline','dtype','gpu_launches')})
-print('e2e', d['e2e']); print('roofline', d['roofline']); print('cpu', d['cpu_baseline']); print('clocks', d['clocks'])
+d=json.loads(open('gpurun_out/bench_w.json').read())
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], {k:(round(v['ms_per_step'],2)) for k,v in d['breakdown'].items()}, d['clocks'])
+for r in json.load(open("gpurun_out/detail.json"))[:10]:
+    print(f"{r['ms_per_step']:8.3f} ms/step  x{r['launches']:3d}  avg {r['avg_ms']:.3f} ms  {r['tflops'] or 0:7.1f} TF/s  {r['sig']}")
 PY

@@ -283,7 +283,30 @@ def chk_im2col():
     return _cmp("im2col", out, ref, 0, 0)
 
 
+def chk_gemm_resid_f32(M, N, K, gamma=True, cg=0):
+    """EPI_RESID_F32: x (fp32, in place) += gamma * (A W^T + b) -- the residual update of block.py:105-106."""
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(23)
+    A = (torch.randn(M, K, generator=g, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(N, K, generator=g, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g, device="cuda") * 0.1
+    gam = (1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")) if gamma else None
+    x = torch.randn(M, N, generator=g, device="cuda") * 2
+    ref = A.float() @ Wt.float().t() + bias
+    if gamma:
+        ref = ref * gam
+    ref = x + ref
+    out = x.clone()
+    ops.gemm(A, Wt, epi=L.EPI_RESID_F32, bias=bias, gamma=gam, out_f32=out, ldo=N, force_cg=cg)
+    torch.cuda.synchronize()
+    return _cmp("resid_f32", out, ref, 2e-3, 2e-3)
+
+
 CHECKS = {
+    "gemm_resid_f32": lambda: chk_gemm_resid_f32(1370 * 3, 1024, 1024),
+    "gemm_resid_f32_cg2": lambda: chk_gemm_resid_f32(1370 * 3, 1024, 4096, cg=2),
+    "gemm_resid_f32_ragged": lambda: chk_gemm_resid_f32(777, 384, 1536, gamma=False),
+    "gemm_resid_f32_small": lambda: chk_gemm_resid_f32(100, 96, 64),
     "gemm_small_bn128": lambda: chk_gemm(300, 256, 128, 128, "bias"),
     "gemm_small_bn256": lambda: chk_gemm(300, 256, 128, 256, "bias"),
     "gemm_small_bn64": lambda: chk_gemm(300, 256, 192, 64, "bias"),
