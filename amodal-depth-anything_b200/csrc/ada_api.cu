@@ -1056,13 +1056,20 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     ADA_CHECK_CUDA(cudaMemcpyAsync(m->tokens_dbg, m->x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, st));
 
   // ---- encoder blocks (block.py:82-107 eval branch). The fp32 stream x is only touched by the LayerNorm kernel:
-  //      the fp32 residual stream x is updated in place by the proj / fc2 GEMM epilogues (EPI_RESID_F32: the x tile
-  //      travels through TMA-staged shared memory, coalesced and under the GEMM's tensor time); the LayerNorm kernels only
-  //      read x and write the bf16 normalised activations (6 bytes per element).
+  //      default: the attention branch leaves gamma1 * (W h + b) in `ybuf` and the MLP branch gamma2 * (...) in `ybuf2`
+  //      (bf16); norm2 normalises x + ybuf without storing it, the NEXT block's norm1 (or the tap norm) adds both and
+  //      norm1 stores x <- (x + ybuf) + ybuf2 (block.py:105-106): one fp32 write of the stream per block, all of it in the
+  //      coalesced LayerNorm kernel.
+  //      ADA_RESID_EPI=1: x is instead updated in place by the proj / fc2 GEMM epilogues (EPI_RESID_F32, x tiles staged
+  //      through TMA) and the LayerNorm kernels only read x. Measured on the same box (batch 32): LayerNorm 4.4 -> 2.45 ms
+  //      but fc2 6.2 -> 7.25 ms and proj 1.9 -> 2.6 ms (the fp32 staging costs pipeline stages and the GEMMs then carry
+  //      the stream's HBM traffic): 658 vs 665 img/s, so it stays off.
+  static const int resid_epi = env_int("ADA_RESID_EPI", 0);
   int tap_i = 0;
+  const __nv_bfloat16 *pend1 = nullptr, *pend2 = nullptr;  // residual-branch outputs not yet added to x
   for (int i = 0; i < c.depth; ++i) {
     const BlockW& w = m->blocks[i];
-    launch_layernorm(m->x, nullptr, nullptr, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, 0, st);
+    launch_layernorm(m->x, pend1, pend2, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, pend1 != nullptr, st);
     {
       GemmArgs e{};
       e.epi = EPI_BF16;
@@ -1074,14 +1081,19 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     launch_attention(m->qkv, m->att, B, N, heads, st);
     {
       GemmArgs e{};
-      e.epi = EPI_RESID_F32;  // x += gamma1 * (att W^T + b), in place through TMA (block.py:105)
       e.bias = w.bproj;
       e.gamma = w.g1;
-      e.out_f32 = m->x;
       e.ldo = D;
+      if (resid_epi) {
+        e.epi = EPI_RESID_F32;  // x += gamma1 * (att W^T + b), in place through TMA (block.py:105)
+        e.out_f32 = m->x;
+      } else {
+        e.epi = EPI_BF16;
+        e.out_bf16 = m->ybuf;
+      }
       linear(m->att, M, D, D, w.wproj, D, D, e, st);
     }
-    launch_layernorm(m->x, nullptr, nullptr, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 0, st);
+    launch_layernorm(m->x, resid_epi ? nullptr : m->ybuf, nullptr, w.ln2w, w.ln2b, m->xn, M, D, 1e-6f, N, 0, 0, st);
     const int Hd = c.ffn_hidden;
     {
       GemmArgs e{};
@@ -1099,16 +1111,26 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     }
     {
       GemmArgs e{};
-      e.epi = EPI_RESID_F32;  // x += gamma2 * (h W^T + b) (block.py:106)
       e.bias = w.b2;
       e.gamma = w.g2;
-      e.out_f32 = m->x;
       e.ldo = D;
+      if (resid_epi) {
+        e.epi = EPI_RESID_F32;  // x += gamma2 * (h W^T + b) (block.py:106)
+        e.out_f32 = m->x;
+      } else {
+        e.epi = EPI_BF16;
+        e.out_bf16 = m->ybuf2;
+      }
       linear(m->hbuf, M, Hd, Hd, w.w2, D, Hd, e, st);
     }
+    if (!resid_epi) {
+      pend1 = m->ybuf;
+      pend2 = m->ybuf2;
+    }
     if (tap_i < 4 && i == c.taps[tap_i]) {
-      // shared final norm, cls dropped, NHWC patch map (dinov2.py:337-340)
-      launch_layernorm(m->x, nullptr, nullptr, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
+      // shared final norm of x (+ both pending branches), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is
+      // updated by the next block's first LayerNorm, so nothing is written back here
+      launch_layernorm(m->x, pend1, pend2, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
       ++tap_i;
     }
   }

@@ -87,6 +87,9 @@ struct GemmArgs {
   int debug_timeline;       // bring-up: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase into g_dev_timeline
 };
 
+#ifndef ADA_RESID_BUFS
+#define ADA_RESID_BUFS 2
+#endif
 template <int BN, int CG, int EPI = 0>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -96,7 +99,7 @@ struct GemmCfg {
   // epilogue staging: one 4 KB buffer per epilogue warp for the 256-wide tiles (two 64-column groups per warp and a long
   // main loop hide the TMA-store drain), two for narrower tiles (small-K, store-bound GEMMs: a single buffer made every
   // tile wait ~1 us for the previous store to release it)
-  static constexpr int kStgBufs = (EPI == EPI_RESID_F32) ? 3 : (BN == 256) ? 1 : 2;  // RESID_F32: load-ahead + store-behind
+  static constexpr int kStgBufs = (EPI == EPI_RESID_F32) ? ADA_RESID_BUFS : (BN == 256) ? 1 : 2;  // RESID_F32: load-ahead (+ store-behind)
   static constexpr int kStagesFit = (232448 - 8 * kStgBufs * 4096 - 2 * 256 * 4 - 512) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
@@ -161,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 4);
   // EPI_RESID_F32: one load barrier per epilogue warp and staging buffer
-  auto xld_bar = [&](int w, int b) { return bar_base + 8u * (2 * Cfg::kStages + 6 + w * 3 + b); };
+  auto xld_bar = [&](int w, int b) { return bar_base + 8u * (2 * Cfg::kStages + 6 + w * 3 + b); };  // up to 3 per warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if constexpr (EPI == EPI_RESID_F32) {
       for (int w = 0; w < 8; ++w)
-        for (int b = 0; b < 3; ++b) mbar_init(xld_bar(w, b), 1);
+        for (int b = 0; b < Cfg::kStgBufs; ++b) mbar_init(xld_bar(w, b), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -367,6 +370,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         named_bar_sync(1, kEpiThreads);
       }
 
+      // EPI_RESID_F32: this warp's blocks of the tile are 32 rows x 32 fp32 columns (one 4 KB staging buffer, 128-byte
+      // rows); column groups cg = half, half + 2, ... of 64 columns, two blocks per group.
+      const int ew = warp - 4;
+      const int xrow0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32;
+      int nblk = 0;
+      auto blk_col = [&](int k) { return n0 + (half + 2 * (k >> 1)) * 64 + (k & 1) * 32; };
+      auto fetch = [&](int k, int b) {  // x block k -> staging buffer b (whole warp, elected lane)
+        mbar_expect_tx_w(xld_bar(ew, b), 4096);
+        tma_load_2d_w(buf0 + static_cast<uint32_t>(b) * 4096u, &tmap_c, xld_bar(ew, b), blk_col(k), xrow0);
+      };
+      if constexpr (EPI == EPI_RESID_F32) {
+        for (int cg = half; cg < BN / 64; cg += 2)
+          if (n0 + cg * 64 < g.N) nblk += 2;
+        // the first block is fetched before the accumulator is complete: its latency hides under the main loop's tail
+        if (nblk > 0) {
+          bulk_wait_read_w<Cfg::kStgBufs - 2>();  // earlier stores that may still read this buffer have drained
+          __syncwarp();
+          fetch(0, xbuf);
+        }
+        // pull the NEXT tile's x blocks of this warp into L2 now: a whole tile period ahead of their use
+        const int tn = t + num_units;
+        if (tn < num_tiles) {
+          const int mtn = tn / tiles_n, n0n = (tn % tiles_n) * BN;
+          const int rown = (mtn * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32;
+          for (int cg = half; cg < BN / 64; cg += 2) {
+            if (n0n + cg * 64 < g.N) {
+              tma_prefetch_l2_2d_w(&tmap_c, n0n + cg * 64, rown);
+              tma_prefetch_l2_2d_w(&tmap_c, n0n + cg * 64 + 32, rown);
+            }
+          }
+        }
+      }
       stamp(1);
       mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
       tc_fence_after();
@@ -491,31 +526,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       } else if constexpr (EPI == EPI_RESID_F32) {
         if constexpr (BN >= 64) {
-          // This warp's blocks of the tile: 32 rows x 32 fp32 columns each (one 4 KB staging buffer, 128-byte rows),
-          // column groups cg = half, half + 2, ... of 64 columns, two blocks per group.
-          const int ew = warp - 4;
-          const int row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32;
-          int nblk = 0;
-          for (int cg = half; cg < BN / 64; cg += 2)
-            if (n0 + cg * 64 < g.N) nblk += 2;
-          auto blk_col = [&](int k) { return n0 + (half + 2 * (k >> 1)) * 64 + (k & 1) * 32; };
-          auto fetch = [&](int k, int b) {  // x block k -> staging buffer b (whole warp, elected lane)
-            mbar_expect_tx_w(xld_bar(ew, b), 4096);
-            tma_load_2d_w(buf0 + static_cast<uint32_t>(b) * 4096u, &tmap_c, xld_bar(ew, b), blk_col(k), row0);
-          };
-          // the first block is fetched before the accumulator is complete: the read of x overlaps the main loop's tail
-          if (nblk > 0) {
-            bulk_wait_read_w<1>();  // at most one earlier store may still be reading shared memory (another buffer)
-            __syncwarp();
-            fetch(0, xbuf);
-          }
-          // (the mbar_wait on tfull above already happened: accumulators are ready)
 #pragma unroll 1
           for (int k = 0; k < nblk; ++k) {
             const int b = xbuf;
-            const int bn_ = (b == 2) ? 0 : b + 1;
-            if (k + 1 < nblk) {  // prefetch the next block; its buffer was last read by the store issued two blocks ago
-              bulk_wait_read_w<1>();
+            const int bn_ = (b == Cfg::kStgBufs - 1) ? 0 : b + 1;
+            if (k + 1 < nblk) {  // prefetch the next block once the store that last read its buffer has drained
+              bulk_wait_read_w<Cfg::kStgBufs - 2>();
               __syncwarp();
               fetch(k + 1, bn_);
             }
@@ -544,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             fence_proxy_async_smem();
             __syncwarp();
-            tma_store_2d_commit_w(&tmap_c, buf, blk_col(k), row0);  // clips rows >= M and columns >= N
+            tma_store_2d_commit_w(&tmap_c, buf, blk_col(k), xrow0);  // clips rows >= M and columns >= N
             xbuf = bn_;
           }
         }

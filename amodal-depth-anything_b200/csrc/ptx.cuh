@@ -237,6 +237,12 @@ __device__ __forceinline__ void tma_load_2d_w(uint32_t dst, const CUtensorMap* m
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// L2 prefetch of one box of a tensor map (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d_w(const CUtensorMap* m, int c0, int c1) {
+  asm volatile(ADA_ELECT_ASM("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];")
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       ADA_ELECT_ASM("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];")
