@@ -42,8 +42,9 @@ struct AttArgs {
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
-// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product, 1 = every exponential on MUFU, 2 = exponentials
-// replaced by a copy (timing skeleton only, wrong results), 3/4/5 = other FMA-pipe fractions, 10 = clock64 timeline.
+// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product (6 of every 16 exponential pairs, evenly spaced, on the
+// FMA pipe), 1 = every exponential on MUFU, 3 = 6/16 clustered, 4 = 8/16, 5 = 4/16, 2 = exponentials replaced by a copy
+// (timing skeleton only, wrong results), 10 = clock64 timeline of one softmax thread and of the issuer thread.
 template <bool B>
 struct IntTag {
   static constexpr bool value = B;
@@ -230,10 +231,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       const float mc = m_used * c;
       // Scale-and-shift and the row sums run as packed pairs (FFMA2 / FADD2: 182 M instead of 267 M warp instructions per
       // launch at B=32); kEmuMask picks the pairs (of the 16 in a 32-column half) whose exponential is evaluated on the
-      // FMA pipe instead of MUFU. Measured (B=32, N=1370): none 0.379 ms, 4/16 0.371, 6/16 0.381, 8/16 0.410 -- the loop
-      // is latency bound (issue 46-60 %, MUFU 40-64 %), see profiles/README.md.
+      // FMA pipe instead of MUFU. Measured stand-alone (B=32, N=1370): none 0.379 ms, 4/16 0.371, 6/16 0.381, 8/16 0.410;
+      // inside the model (1.55 GHz, power capped), ms per step over the 24 launches: none 12.3, 4/16 (every 4th pair) 11.4,
+      // 6/16 clustered 11.8, 6/16 evenly spaced (the product mask) 11.15, 8/16 12.8. See profiles/README.md.
       constexpr uint32_t kEmuMask = (VARIANT == 1) ? 0u : (VARIANT == 3) ? 0x5252u : (VARIANT == 4) ? 0x5555u
-                                  : (VARIANT == 5) ? 0x9249u : 0x1111u;
+                                  : (VARIANT == 5) ? 0x1111u : 0x9249u;
       const uint64_t c2 = f2_pack(c, c), nmc2 = f2_pack(-mc, -mc);
       uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};  // independent packed row-sum chains
       uint32_t pk[32];
