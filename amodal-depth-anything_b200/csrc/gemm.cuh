@@ -90,6 +90,9 @@ struct GemmArgs {
 #ifndef ADA_RESID_BUFS
 #define ADA_RESID_BUFS 2
 #endif
+#ifndef ADA_STG256
+#define ADA_STG256 1
+#endif
 template <int BN, int CG, int EPI = 0>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -99,7 +102,7 @@ struct GemmCfg {
   // epilogue staging: one 4 KB buffer per epilogue warp for the 256-wide tiles (two 64-column groups per warp and a long
   // main loop hide the TMA-store drain), two for narrower tiles (small-K, store-bound GEMMs: a single buffer made every
   // tile wait ~1 us for the previous store to release it)
-  static constexpr int kStgBufs = (EPI == EPI_RESID_F32) ? ADA_RESID_BUFS : (BN == 256) ? 1 : 2;  // RESID_F32: load-ahead (+ store-behind)
+  static constexpr int kStgBufs = (EPI == EPI_RESID_F32) ? ADA_RESID_BUFS : (BN == 256) ? ADA_STG256 : 2;  // RESID_F32: load-ahead (+ store-behind)
   static constexpr int kStagesFit = (232448 - 8 * kStgBufs * 4096 - 2 * 256 * 4 - 512) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStages = 2;
