@@ -1,14 +1,9 @@
-cp amodal-depth-anything_b200/libamodal_b200.so /tmp/lib_keep.so
-for rep in 1 2; do for v in s1 s2; do
-cp tools/ab/lib_$v.so amodal-depth-anything_b200/libamodal_b200.so
-timeout 300 python bench.py --no-cpu-baseline --steps 8 --detail gpurun_out/detail.json 2>&1 | tail -1 > gpurun_out/bench_w.json; python - $v <<'PY'
-import json,sys
-d=json.loads(open('gpurun_out/bench_w.json').read())
-rows=json.load(open("gpurun_out/detail.json"))
-def f(sub):
-    r=[x for x in rows if sub in x['sig']]
-    return round(r[0]['ms_per_step'],2) if r else None
-print(sys.argv[1], round(d['value'],1), round(d['ms_per_step'],2), 'lin', round(d['breakdown']['gemm_tcgen05_linear']['ms_per_step'],2), 'conv', round(d['breakdown']['gemm_tcgen05_conv3x3']['ms_per_step'],2), 'fc2', f('N=1024 K=4096'), 'proj', f('M=43840 N=1024 K=1024'), 'fc1', f('N=4096 K=1024'), 'qkv', f('N=3072 K=1024'), d['clocks']['sm_mhz'] if d['clocks'] else None)
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 300 gpurun_out/bench_default.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('metric','value','unit','n_gpus','steps','warmup','ms_per_step','scaling','vs_baseline','dtype','gpu_launches')})
+print('e2e', d['e2e']['value'], 'roofline', d['roofline']['achieved'], d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'], 'clocks', d['clocks'])
 PY
-done; done
-cp /tmp/lib_keep.so amodal-depth-anything_b200/libamodal_b200.so
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-300
