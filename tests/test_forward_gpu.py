@@ -212,3 +212,23 @@ def test_cuda_graph_replay_is_bit_identical():
             assert torch.equal(_run(m, inp), ref)
     m.set_graph(False)
     assert torch.equal(_run(m, b), eager[1])
+
+
+def test_streamed_inference_matches_direct_calls():
+    """pipeline.StreamedInference (what bench.py's e2e figure runs): pinned host batches in, pinned host results out, H2D /
+    forward / D2H on three streams with double-buffered device inputs. Every batch must equal the direct model call."""
+    from amodal_depth_anything_b200.pipeline import StreamedInference
+    sd = synth.make_state_dict("vits", "mask+observation", 12)
+    m = _model("vits", "mask+observation", "invisible_part", sd)
+    batches = [synth.make_inputs(2, 126, 98, s) for s in (31, 32, 33, 34, 35)]
+    want = [_run(m, b) for b in batches]
+    host_in = [(b["x"].pin_memory(), b["guide_mask"].pin_memory(), b["observation"].pin_memory()) for b in batches]
+    host_out = [torch.empty(2, 1, 126, 98).pin_memory() for _ in batches]
+    runner = StreamedInference(m)
+    for _ in range(2):  # second pass reuses the device slots
+        for o in host_out:
+            o.zero_()
+        runner.run(iter(host_in), host_out)
+        torch.cuda.synchronize()
+        for got, ref in zip(host_out, want):
+            assert torch.equal(got, ref)
