@@ -232,3 +232,17 @@ def test_streamed_inference_matches_direct_calls():
         torch.cuda.synchronize()
         for got, ref in zip(host_out, want):
             assert torch.equal(got, ref)
+
+
+def test_forward_matches_oracle_non_square_518x686():
+    """The un-guided model's own resize rule (depth_anything_v2_raw/dpt.py:196-205) turns a 480x640 photo into 518x686:
+    37x49 patches, pyramid 148x196 / 74x98 / 37x49 / 19x25 -- ragged conv tiles in both directions and a position table
+    interpolated to a non-square grid (dinov2.py:199-230)."""
+    sd = synth.make_state_dict("vits", "mask+observation", 19)
+    inp = synth.make_inputs(1, 518, 686, 19)
+    m = _model("vits", "mask+observation", "invisible_part", sd)
+    out = _run(m, inp)
+    ref = O.forward(sd, "vits", "mask+observation", inp["x"], None, inp["guide_mask"], inp["observation"])
+    rel, absrel = _errors(out, ref, inp["mask01"])
+    print("vits 518x686", f"rel {rel:.3e} absrel {absrel:.3e}")
+    assert rel <= REL_TOL and absrel <= ABSREL_TOL
