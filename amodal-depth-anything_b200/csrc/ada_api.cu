@@ -95,6 +95,31 @@ static int env_int(const char* name, int dflt) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM launcher
+// Programmatic dependent launch: GEMM / LayerNorm / attention launches carry the programmatic-stream-serialization
+// attribute (their kernels call griddepcontrol.wait after the prologue), so a kernel's prologue overlaps its predecessor's
+// tail. Measured: ViT-L, one image 3.74 -> 3.37 ms; at batch 32 it costs ~1 % (early CTAs of the next kernel compete with
+// the draining one). ADA_PDL = 1 / 0 forces it on / off; default: on for small token counts only (set per forward).
+static bool g_pdl_now = false;
+static bool pdl_enabled() { return g_pdl_now; }
+static void pdl_select(long long tokens) {
+  static const int v = env_int("ADA_PDL", -1);
+  g_pdl_now = (v < 0) ? (tokens <= 3000) : (v != 0);
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ADA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 template <int BN, int CG, int EPI>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                            const GemmArgs& g, int num_tiles, cudaStream_t st) {
@@ -111,13 +136,22 @@ static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const C
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   ADA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, EPI>, ta, tb, tc, tc2, g));
 }
 
@@ -345,10 +379,10 @@ static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bf
   ProfScope prof(PC_LAYERNORM, 0.0,
                  (6.0 + (delta ? 2.0 : 0.0) + (delta2 ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0)) * rows * static_cast<double>(D), st);
   switch (D / 128) {
-    case 3: layernorm_rows_kernel<3><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 6: layernorm_rows_kernel<6><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 8: layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 12: layernorm_rows_kernel<12><<<grid, 256, 0, st>>>(x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 3: launch_pdl(layernorm_rows_kernel<3>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 6: launch_pdl(layernorm_rows_kernel<6>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 8: launch_pdl(layernorm_rows_kernel<8>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    case 12: launch_pdl(layernorm_rows_kernel<12>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
     default: throw AdaError(ADA_EINVAL, "layernorm: embed_dim must be 384/768/1024/1536");
   }
   ADA_REQUIRE(D % 128 == 0, "layernorm: D % 128");
@@ -390,7 +424,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-#define ADA_ATT_LAUNCH(V, SMEM) attention_tcgen05_kernel<V><<<grid, kAttThreads, SMEM, st>>>(tm, tmo, a)
+#define ADA_ATT_LAUNCH(V, SMEM) launch_pdl(attention_tcgen05_kernel<V>, grid, dim3(kAttThreads), SMEM, st, tm, tmo, a)
   switch (variant) {
     case 1: ADA_ATT_LAUNCH(1, kAttSmemBytes); break;
     case 2: ADA_ATT_LAUNCH(2, kAttSmemBytes); break;
@@ -1033,6 +1067,7 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   ensure_workspace(m, B, H, W);
   ada_model::PosCache& pc = get_pos(m, gh, gw);
   g_launches = 0;
+  pdl_select(static_cast<long long>(M));
   struct ProfGuard {
     ProfGuard(Profiler* p) { g_prof = p; }
     ~ProfGuard() { g_prof = nullptr; }

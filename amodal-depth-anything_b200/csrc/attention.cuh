@@ -96,6 +96,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
+  griddep_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;

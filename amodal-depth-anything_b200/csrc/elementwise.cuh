@@ -27,6 +27,8 @@ layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ d
                       const __nv_bfloat16* __restrict__ delta2, const float* __restrict__ w, const float* __restrict__ b,
                       __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls, int write_x) {
   constexpr int D = CHUNKS * 128;
+  griddep_wait();
+  griddep_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;

@@ -203,6 +203,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  griddep_wait();               // (programmatic dependent launch) everything above overlapped the previous kernel's tail
+  griddep_launch_dependents();  // the next kernel may start its own prologue as SMs free up
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
