@@ -97,13 +97,14 @@ static int env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------------ GEMM launcher
 // Programmatic dependent launch: GEMM / LayerNorm / attention launches carry the programmatic-stream-serialization
 // attribute (their kernels call griddepcontrol.wait after the prologue), so a kernel's prologue overlaps its predecessor's
-// tail. Measured: ViT-L, one image 3.74 -> 3.37 ms; at batch 32 it costs ~1 % (early CTAs of the next kernel compete with
-// the draining one). ADA_PDL = 1 / 0 forces it on / off; default: on for small token counts only (set per forward).
+// tail. Measured (ViT-L 518^2, ms per step off -> on): batch 1 3.74 -> 3.37, 2 4.63 -> 4.36, 4 7.37 -> 7.18, 8 13.13 -> 12.98,
+// 16 25.10 -> 25.10, 32 +1 % (early CTAs of the next kernel compete with the draining one). ADA_PDL = 1 / 0 forces it
+// on / off; default: on up to 12000 tokens (set per forward).
 static bool g_pdl_now = false;
 static bool pdl_enabled() { return g_pdl_now; }
 static void pdl_select(long long tokens) {
   static const int v = env_int("ADA_PDL", -1);
-  g_pdl_now = (v < 0) ? (tokens <= 3000) : (v != 0);
+  g_pdl_now = (v < 0) ? (tokens <= 12000) : (v != 0);
 }
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
