@@ -203,8 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  griddep_wait();               // (programmatic dependent launch) everything above overlapped the previous kernel's tail
-  griddep_launch_dependents();  // the next kernel may start its own prologue as SMs free up
+  griddep_wait();  // (programmatic dependent launch) everything above overlapped the previous kernel's tail
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -226,6 +225,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
+      // let the next kernel's CTAs be scheduled once every CTA of this grid is on its LAST tile: its prologue then runs
+      // on SMs that drain early instead of competing with full waves (an immediate trigger cost ~1 % at batch 32)
+      if (t + num_units >= num_tiles) griddep_launch_dependents();
       const int mt = t / tiles_n, nt = t % tiles_n;
       int img = 0, y0 = 0, x0 = 0;
       if (g.a_mode == A_CONV3X3) {
