@@ -100,7 +100,7 @@ static int env_int(const char* name, int dflt) {
 // tail. Measured (ViT-L 518^2, ms per step off -> on): batch 1 3.74 -> 3.37, 2 4.63 -> 4.36, 4 7.37 -> 7.18, 8 13.13 -> 12.98,
 // 16 25.10 -> 25.10, 32 +1 % (early CTAs of the next kernel compete with the draining one). ADA_PDL = 1 / 0 forces it
 // on / off; default: on up to 12000 tokens (set per forward).
-static bool g_pdl_now = false;
+static thread_local bool g_pdl_now = false;  // per calling thread: handles may be driven from different threads
 static bool pdl_enabled() { return g_pdl_now; }
 static void pdl_select(long long tokens) {
   static const int v = env_int("ADA_PDL", -1);
@@ -183,7 +183,7 @@ struct GemmLaunch {
 };
 
 
-static int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
+static thread_local int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
 
 // ---- optional per-launch CUDA-event profiler (bench.py's roofline / breakdown; off in the headline timing loop)
 enum ProfClass : int { PC_GEMM_LINEAR = 0, PC_GEMM_CONV, PC_ATTENTION, PC_LAYERNORM, PC_CHANNEL_LN, PC_UPSAMPLE, PC_GATHER, PC_COUNT };
@@ -196,7 +196,7 @@ struct ProfRec {
 struct Profiler {
   std::vector<ProfRec> recs;
 };
-static Profiler* g_prof = nullptr;
+static thread_local Profiler* g_prof = nullptr;
 struct ProfScope {
   ProfRec* r = nullptr;
   cudaStream_t st;
