@@ -104,6 +104,20 @@ def cpu_reference_rate(encoder, size, steps, warmup):
     return 1.0 / sec, sec, torch.get_num_threads()
 
 
+def cpu_context():
+    """SURVEY.md section 8d asks for the CPU model and the ViT-S 518x518 single-image time next to the baseline."""
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    _, sec_s, _ = cpu_reference_rate("vits", 518, 5, 1)
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "vits_518_b1_s_per_image": sec_s}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -304,7 +318,7 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, sec, cores = cpu_reference_rate(a.encoder, a.size, 3, 1)
-        cpu_base = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+        cpu_base = {"context": cpu_context(), "value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                     "sample": f"3 images of the same workload ({a.encoder} {a.size}x{a.size}, batch 1 per step, fp32 torch CPU "
                               f"oracle) after 1 warm-up, {sec:.2f} s/image"}
 
