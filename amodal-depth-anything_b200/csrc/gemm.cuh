@@ -2,6 +2,10 @@
 //
 //   warp 0      : TMA producer  (A and B tiles, 128-byte swizzle, 4..8 stage mbarrier ring)
 //   warp 1      : MMA issuer    (tcgen05.mma, 128 x BN x 16 per CTA, fp32 accumulators in TMEM, 2 accumulator stages)
+//                 Both run their loops with the whole warp converged and ONE elect.sync-predicated lane per TMA / tcgen05
+//                 instruction (ptx.cuh *_w wrappers): inside `if (lane == 0)` the compiler builds an ELECT / R2UR /
+//                 BRA.U.ANY waterfall around every descriptor (13-22 instructions per MMA) and, competing for issue slots
+//                 with the epilogue warps of the same scheduler, one MMA issue took ~160 cycles -- longer than the MMA.
 //   warp 2      : TMEM allocator
 //   warps 4..11 : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem -> TMA store);
 //                                 two warpgroups split the tile's 64-column groups: ncu showed the 4-warp epilogue
@@ -23,6 +27,9 @@
 // ~45% of the K=4096 rate). Instead every epilogue warp converts 64 columns at a time, writes its 32x64 bf16 block
 // into a private 4 KB swizzled staging buffer (conflict-free 16-byte stores) and one lane issues a TMA store; the
 // hardware clips rows/columns/pixels that fall outside the tensor, so ragged M, N, H, W need no predication.
+// The arithmetic is packed fp32 (fma.rn.f32x2) and activation / residual handling are template parameters (EpiMode), so
+// the plain path costs 1.6 instructions per output. Shared-memory bandwidth is the scarce resource of the 256-wide main
+// loop (~125 B/clk of TMA writes + MMA reads): epilogue staging traffic is kept to 4 KB per 64 columns and warp.
 //
 // Reference ops this kernel replaces (all fp32 torch ops in the reference):
 //   attention.py:51,60  mlp.py:36-39  swiglu_ffn.py:30-33  layer_scale.py:28                     (encoder linears)
