@@ -9,7 +9,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -52,6 +55,10 @@ static inline uint16_t f2bf(float f) {  // round-to-nearest-even, same as __floa
 }
 
 // ------------------------------------------------------------------------------------------------ device context
+// Everything that CUDA keeps per device (SM count, the opt-in shared-memory size of each kernel) is keyed by the device
+// ordinal that is current on the calling thread: one process may drive several GPUs, one handle each (SURVEY.md section 5,
+// "one process, 8 streams"), and handles may be driven from different threads.
+constexpr int kMaxDevices = 64;
 struct DeviceInfo {
   int device = -1;
   int sms = 0;
@@ -59,34 +66,50 @@ struct DeviceInfo {
   std::string why;
 };
 static DeviceInfo& device_info() {
-  static DeviceInfo di;
-  static bool init = false;
-  if (!init) {
-    init = true;
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-      di.why = std::string("no CUDA device: ") + cudaGetErrorString(e);
-      cudaGetLastError();
-      return di;
-    }
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static DeviceInfo table[kMaxDevices];
+  static std::once_flag once[kMaxDevices];
+  static DeviceInfo none;
+  static std::once_flag none_once;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    cudaGetLastError();
+    std::call_once(none_once, [&] { none.why = std::string("no CUDA device: ") + cudaGetErrorString(e); });
+    return none;
+  }
+  std::call_once(once[dev], [&] {
+    DeviceInfo& di = table[dev];
     cudaDeviceProp p;
-    cudaGetDeviceProperties(&p, dev);
+    cudaError_t pe = cudaGetDeviceProperties(&p, dev);
+    if (pe != cudaSuccess) {
+      cudaGetLastError();
+      di.why = std::string("no CUDA device: ") + cudaGetErrorString(pe);
+      return;
+    }
     if (p.major != 10) {
       di.why = "device is sm_" + std::to_string(p.major) + std::to_string(p.minor) + ", this library is sm_100a only";
-      return di;
+      return;
     }
     di.device = dev;
     di.sms = p.multiProcessorCount;
     di.ok = true;
-  }
-  return di;
+  });
+  return table[dev];
 }
 static void require_device() {
   DeviceInfo& di = device_info();
   if (!di.ok) throw AdaError(ADA_ENODEVICE, di.why);
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: `done` is a per-kernel bit mask of the device
+// ordinals it has been set on (setting it twice from two racing threads is harmless).
+template <typename K>
+static void ensure_smem_attr(K kernel, int bytes, std::atomic<uint64_t>& done) {
+  const int dev = device_info().device;
+  if (dev < 0) throw AdaError(ADA_ENODEVICE, device_info().why);
+  const uint64_t bit = 1ull << dev;
+  if (done.load(std::memory_order_acquire) & bit) return;
+  ADA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.fetch_or(bit, std::memory_order_release);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -125,12 +148,8 @@ template <int BN, int CG, int EPI>
 static void launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                            const GemmArgs& g, int num_tiles, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CG, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(gemm_tcgen05_kernel<BN, CG, EPI>, Cfg::kSmemBytes, attr_done);
   const int units = std::min(num_tiles, device_info().sms / CG);  // persistent: one CTA (or CTA pair) per SM (pair)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
@@ -186,7 +205,7 @@ struct GemmLaunch {
 static thread_local int g_launches = 0;  // counted per forward (host side, single-threaded per handle)
 
 // ---- optional per-launch CUDA-event profiler (bench.py's roofline / breakdown; off in the headline timing loop)
-enum ProfClass : int { PC_GEMM_LINEAR = 0, PC_GEMM_CONV, PC_ATTENTION, PC_LAYERNORM, PC_CHANNEL_LN, PC_UPSAMPLE, PC_GATHER, PC_COUNT };
+enum ProfClass : int { PC_GEMM_LINEAR = 0, PC_GEMM_CONV, PC_ATTENTION, PC_LAYERNORM, PC_CHANNEL_LN, PC_UPSAMPLE, PC_GATHER, PC_TAIL_GATHER, PC_COUNT };
 struct ProfRec {
   int cls;
   double flops, bytes;
@@ -274,10 +293,14 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   // output maps for the TMA-store epilogues (dummy = tb otherwise; never dereferenced)
   CUtensorMap tc = tb, tc2 = tb;
   g.has_relu_copy = 0;
+#ifdef ADA_BRINGUP
   {
     static const int dbg = env_int("ADA_GEMM_TIMELINE", 0);
     g.debug_timeline = dbg;
   }
+#else
+  g.debug_timeline = 0;
+#endif
   if (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU) {
     const int n_out = (g.epi == EPI_SWIGLU) ? L.N / 2 : L.N;
     ADA_REQUIRE(g.out_bf16 != nullptr && g.ldo % 8 == 0 && n_out % 8 == 0, "bf16 output needs ldo, N multiples of 8");
@@ -392,22 +415,6 @@ static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bf
 }
 
 static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st) {
-  static bool attr_set = false;
-  static int variant = 0;
-  if (!attr_set) {
-    variant = env_int("ADA_ATT_VARIANT", 0);
-#define ADA_ATT_ATTR(V) \
-  ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes))
-    ADA_ATT_ATTR(0);
-    ADA_ATT_ATTR(1);
-    ADA_ATT_ATTR(2);
-    ADA_ATT_ATTR(3);
-    ADA_ATT_ATTR(4);
-    ADA_ATT_ATTR(5);
-#undef ADA_ATT_ATTR
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes + 40000));
-    attr_set = true;
-  }
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
@@ -425,17 +432,31 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-#define ADA_ATT_LAUNCH(V, SMEM) launch_pdl(attention_tcgen05_kernel<V>, grid, dim3(kAttThreads), SMEM, st, tm, tmo, a)
+#ifdef ADA_BRINGUP
+  // measurement variants of the kernel (attention.cuh: exponential placement, timing skeleton, clock64 timeline) exist only
+  // in bring-up builds (-DADA_BRINGUP); the product library carries variant 0 alone.
+  static const int variant = env_int("ADA_ATT_VARIANT", 0);
+#define ADA_ATT_LAUNCH(V, SMEM)                                                                 \
+  do {                                                                                          \
+    static std::atomic<uint64_t> done{0};                                                       \
+    ensure_smem_attr(attention_tcgen05_kernel<V>, SMEM, done);                                  \
+    launch_pdl(attention_tcgen05_kernel<V>, grid, dim3(kAttThreads), SMEM, st, tm, tmo, a);     \
+  } while (0)
   switch (variant) {
     case 1: ADA_ATT_LAUNCH(1, kAttSmemBytes); break;
     case 2: ADA_ATT_LAUNCH(2, kAttSmemBytes); break;
     case 3: ADA_ATT_LAUNCH(3, kAttSmemBytes); break;
     case 4: ADA_ATT_LAUNCH(4, kAttSmemBytes); break;
     case 5: ADA_ATT_LAUNCH(5, kAttSmemBytes); break;
-    case 10: ADA_ATT_LAUNCH(10, kAttSmemBytes + (env_int("ADA_ATT_PAD", 0) ? 40000 : 0)); break;
+    case 10: ADA_ATT_LAUNCH(10, kAttSmemBytes); break;
     default: ADA_ATT_LAUNCH(0, kAttSmemBytes); break;
   }
 #undef ADA_ATT_LAUNCH
+#else
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(attention_tcgen05_kernel<0>, kAttSmemBytes, attr_done);
+  launch_pdl(attention_tcgen05_kernel<0>, grid, dim3(kAttThreads), kAttSmemBytes, st, tm, tmo, a);
+#endif
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }
@@ -472,14 +493,11 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
 
 static void launch_tail_gather(const __nv_bfloat16* V, const float* bias2, const float* aux, float* out, int B, int Hl,
                                int Wl, int H, int W, int sigmoid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADA_CHECK_CUDA(cudaFuncSetAttribute(tail_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(tail_gather_kernel, kTailSmemBytes, attr_done);
   dim3 grid((W + kTailTile - 1) / kTailTile, (H + kTailTile - 1) / kTailTile, B);
-  ProfScope prof(PC_UPSAMPLE, 2.0 * B * static_cast<double>(H) * W * 36.0 * 32.0,
-                 static_cast<double>(B) * (2.0 * Hl * Wl * kTailCh + 4.0 * H * W), st);
+  // HBM-bound: algorithmic bytes = the tap map read once + the fp32 output (its 36 x 32 FMAs per pixel are not counted)
+  ProfScope prof(PC_TAIL_GATHER, 0.0, static_cast<double>(B) * (2.0 * Hl * Wl * kTailCh + 4.0 * H * W), st);
   tail_gather_kernel<<<grid, 256, kTailSmemBytes, st>>>(V, bias2, aux, out, Hl, Wl, H, W, sigmoid);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -631,6 +649,8 @@ struct ada_model;
 namespace ada { struct Profiler; }
 struct ada_model {
   ada_config cfg{};
+  int device = -1;  // device ordinal current at ada_create: weights, workspace and every launch live there
+  std::map<std::string, std::vector<int64_t>> spec;  // expected state dict: name -> shape (expected_weights)
   std::unordered_map<std::string, HostTensor> host;  // raw fp32 state dict (released after finalize)
   bool finalized = false;
   bool capture = false;
@@ -763,8 +783,94 @@ static ConvW up_conv3x3(ada_model* m, const std::string& prefix, int cout, int c
   return c;
 }
 
+// The reference state dict for this architecture (relative to `encoder.`): name -> shape. SURVEY.md section 8b key template;
+// dinov2.py:107-117,188-196 (embeddings), block.py:60-80 (blocks), dpt.py:86-159 (head). ada_set_weight rejects anything
+// that is not in this table (ADA_EINVAL), ada_finalize reports every entry that was never set (ADA_ESTATE).
+static std::map<std::string, std::vector<int64_t>> expected_weights(const ada_config& c) {
+  std::map<std::string, std::vector<int64_t>> w;
+  const int64_t D = c.embed_dim, Cg = c.guide_channels, G = c.pos_grid, F = c.features, Hd = c.ffn_hidden;
+  const std::string pre = "pretrained.";
+  w[pre + "cls_token"] = {1, 1, D};
+  w[pre + "pos_embed"] = {1, 1 + G * G, D};
+  w[pre + "mask_token"] = {1, D};
+  w[pre + "patch_embed.proj.weight"] = {D, 3, 14, 14};
+  w[pre + "patch_embed.proj.bias"] = {D};
+  if (Cg > 0) {
+    w[pre + "patch_embed_guidance.proj.weight"] = {D, Cg, 14, 14};
+    w[pre + "patch_embed_guidance.proj.bias"] = {D};
+  }
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string b = pre + "blocks." + std::to_string(i) + ".";
+    for (const char* n : {"norm1", "norm2"}) {
+      w[b + n + ".weight"] = {D};
+      w[b + n + ".bias"] = {D};
+    }
+    w[b + "attn.qkv.weight"] = {3 * D, D};
+    w[b + "attn.qkv.bias"] = {3 * D};
+    w[b + "attn.proj.weight"] = {D, D};
+    w[b + "attn.proj.bias"] = {D};
+    w[b + "ls1.gamma"] = {D};
+    w[b + "ls2.gamma"] = {D};
+    if (c.ffn_kind == 0) {
+      w[b + "mlp.fc1.weight"] = {Hd, D};
+      w[b + "mlp.fc1.bias"] = {Hd};
+      w[b + "mlp.fc2.weight"] = {D, Hd};
+      w[b + "mlp.fc2.bias"] = {D};
+    } else {
+      w[b + "mlp.w12.weight"] = {2 * Hd, D};
+      w[b + "mlp.w12.bias"] = {2 * Hd};
+      w[b + "mlp.w3.weight"] = {D, Hd};
+      w[b + "mlp.w3.bias"] = {D};
+    }
+  }
+  w[pre + "norm.weight"] = {D};
+  w[pre + "norm.bias"] = {D};
+  const std::string hd = "depth_head.";
+  auto conv = [&](const std::string& name, int64_t co, int64_t ci, int64_t k, bool bias) {
+    w[hd + name + ".weight"] = {co, ci, k, k};
+    if (bias) w[hd + name + ".bias"] = {co};
+  };
+  for (int i = 0; i < 4; ++i) {
+    const int64_t Ci = c.out_channels[i];
+    const std::string si = std::to_string(i);
+    conv("projects." + si, Ci, D, 1, true);
+    if (i == 0) conv("resize_layers.0", Ci, Ci, 4, true);  // ConvTranspose2d: [Cin, Cout, k, k], Cin == Cout
+    if (i == 1) conv("resize_layers.1", Ci, Ci, 2, true);
+    if (i == 3) conv("resize_layers.3", Ci, Ci, 3, true);
+    if (c.input_projection) {
+      conv("input_projection." + si + ".0", Ci, Ci, 3, true);
+      w[hd + "input_projection." + si + ".1.weight"] = {Ci};
+      w[hd + "input_projection." + si + ".1.bias"] = {Ci};
+    }
+    conv("scratch.layer" + std::to_string(i + 1) + "_rn", F, Ci, 3, false);
+  }
+  for (int k = 1; k <= 4; ++k) {
+    const std::string r = "scratch.refinenet" + std::to_string(k) + ".";
+    conv(r + "out_conv", F, F, 1, true);
+    for (const char* u : {"resConfUnit1", "resConfUnit2"})
+      for (const char* cv : {"conv1", "conv2"}) conv(r + u + "." + cv, F, F, 3, true);
+  }
+  conv("scratch.output_conv1", F / 2, F, 3, true);
+  conv("scratch.output_conv2.0", 32, F / 2, 3, true);
+  conv("scratch.output_conv2.2", 1, 32, 1, true);
+  return w;
+}
+
 static void finalize_model(ada_model* m) {
+  {  // report EVERY missing tensor, not just the first one the packer would trip over
+    std::string missing;
+    int n_missing = 0;
+    for (const auto& kv : m->spec)
+      if (!m->host.count(kv.first)) {
+        if (n_missing++ < 24) missing += (missing.empty() ? "" : ", ") + kv.first;
+      }
+    if (n_missing)
+      throw AdaError(ADA_ESTATE, "ada_finalize: " + std::to_string(n_missing) + " of " + std::to_string(m->spec.size()) +
+                                     " tensors were never set: " + missing + (n_missing > 24 ? ", ..." : ""));
+  }
   require_device();
+  if (m->device < 0) m->device = device_info().device;
+  ADA_REQUIRE(device_info().device == m->device, "ada_finalize: the device that was current at ada_create must be current");
   const ada_config& c = m->cfg;
   const int D = c.embed_dim, Cg = c.guide_channels, G = c.pos_grid;
   const std::string pre = "pretrained.";
@@ -896,6 +1002,14 @@ static ada_model::PosCache& get_pos(ada_model* m, int gh, int gw) {
   auto it = m->pos_cache.find(key);
   if (it != m->pos_cache.end()) return it->second;
   const int D = m->cfg.embed_dim, G = m->cfg.pos_grid;
+  if (m->pos_cache.size() >= 16) {  // bounded: a sweep over many resolutions must not grow the cache without limit
+    ADA_CHECK_CUDA(cudaDeviceSynchronize());  // an in-flight forward may still read an entry
+    for (auto& kv : m->pos_cache) {
+      cudaFree(kv.second.posb);
+      cudaFree(kv.second.cls_pos);
+    }
+    m->pos_cache.clear();
+  }
   std::vector<float> pp(static_cast<size_t>(gh) * gw * D);
   if (gh == G && gw == G) {  // dinov2.py:203-204: table used as is
     std::copy(m->pos_host.begin() + D, m->pos_host.end(), pp.begin());
@@ -929,6 +1043,12 @@ struct Bump {
 };
 
 static int down2(int h) { return (h - 1) / 2 + 1; }
+// fused tail (tap GEMM at low resolution + gather) needs the 8h -> 14h geometry; ADA_TAIL=0 selects the unfused path
+// (upsample + implicit-GEMM conv with the EPI_TAIL epilogue), kept for A/B measurements
+static bool tail_fused(int hl, int wl, int H, int W) {
+  static const int tail_mode = env_int("ADA_TAIL", 1);
+  return tail_mode == 1 && hl * 14 == H * 8 && wl * 14 == W * 8;
+}
 
 static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* base) {
   const ada_config& c = m->cfg;
@@ -950,8 +1070,11 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
   m->ybuf = b.take<__nv_bfloat16>(M * D);
   m->ybuf2 = b.take<__nv_bfloat16>(M * D);
   m->a_embed = b.take<__nv_bfloat16>(BP * m->kpad);
-  m->tokens_dbg = b.take<float>(M * D);
-  reg("tokens", m->tokens_dbg, M * D, 1);
+  m->tokens_dbg = nullptr;
+  if (m->capture) {  // test hook only (ada_set_capture re-plans the workspace)
+    m->tokens_dbg = b.take<float>(M * D);
+    reg("tokens", m->tokens_dbg, M * D, 1);
+  }
   for (int i = 0; i < 4; ++i) {
     m->tap[i] = b.take<__nv_bfloat16>(BP * D);
     reg("tap" + std::to_string(i), m->tap[i], BP * D, 0);
@@ -984,14 +1107,22 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
     reg("path_" + std::to_string(k), m->path[k], pix * F, 0);
   }
   m->oc1b = b.take<__nv_bfloat16>(static_cast<size_t>(B) * ph[1] * pw[1] * (F / 2));
-  m->up = b.take<__nv_bfloat16>(static_cast<size_t>(B) * H * W * (F / 2));
+  // the [B,H,W,F/2] upsampled map only exists on the unfused tail path (ADA_TAIL=0); the default fused tail never
+  // materialises it (2.2 GB at ViT-L, batch 32, 518^2)
+  m->up = tail_fused(ph[1], pw[1], H, W) ? nullptr : b.take<__nv_bfloat16>(static_cast<size_t>(B) * H * W * (F / 2));
   m->vtap = b.take<__nv_bfloat16>(static_cast<size_t>(B) * ph[1] * pw[1] * 288);
   return b.off + 1024;
 }
 
-static void ensure_workspace(ada_model* m, int B, int H, int W) {
+// Re-plans the arena when (B,H,W) changes. The previous forward may still be running in the OLD layout on `st` (any
+// non-blocking stream; a ragged last batch of a streamed run): every re-plan first drains `st`, and the one-off memset of
+// the patch matrix' K padding is ordered on `st` as well, so nothing of the new layout is touched before earlier work on
+// the caller's stream has finished. A handle is driven from one stream at a time (include/amodal_b200.h). This is the only
+// host synchronisation ada_forward ever performs, and only on the first call at a new shape.
+static void ensure_workspace(ada_model* m, int B, int H, int W, cudaStream_t st) {
   if (B == m->wsB && H == m->wsH && W == m->wsW) return;
   m->drop_graph();  // a captured graph points into the old workspace layout
+  ADA_CHECK_CUDA(cudaStreamSynchronize(st));
   const size_t need_bytes = plan_workspace(m, B, H, W, true, nullptr);
   if (need_bytes > m->arena.bytes) {
     if (m->arena.p) {
@@ -1005,8 +1136,7 @@ static void ensure_workspace(ada_model* m, int B, int H, int W) {
   }
   plan_workspace(m, B, H, W, false, static_cast<char*>(m->arena.p));
   // zero the K padding of the patch matrix once (the gather never writes it)
-  ADA_CHECK_CUDA(cudaMemset(m->a_embed, 0, static_cast<size_t>(B) * (H / 14) * (W / 14) * m->kpad * 2));
-  ADA_CHECK_CUDA(cudaDeviceSynchronize());
+  ADA_CHECK_CUDA(cudaMemsetAsync(m->a_embed, 0, static_cast<size_t>(B) * (H / 14) * (W / 14) * m->kpad * 2, st));
   m->wsB = B;
   m->wsH = H;
   m->wsW = W;
@@ -1055,6 +1185,8 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
                          float* out, int B, int H, int W, cudaStream_t st) {
   require_device();
   if (!m->finalized) throw AdaError(ADA_ESTATE, "ada_forward before ada_finalize");
+  ADA_REQUIRE(device_info().device == m->device, "ada_forward: the handle was created on device " + std::to_string(m->device) +
+                                                     " but device " + std::to_string(device_info().device) + " is current");
   ADA_REQUIRE(B > 0 && H > 0 && W > 0, "B, H, W must be positive");
   ADA_REQUIRE(H % 14 == 0, "Input image height is not a multiple of patch height 14");
   ADA_REQUIRE(W % 14 == 0, "Input image width is not a multiple of patch width 14");
@@ -1065,7 +1197,7 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   const int D = c.embed_dim, F = c.features, heads = c.num_heads;
   const int gh = H / 14, gw = W / 14, P = gh * gw, N = P + 1;
   const int M = B * N, BP = B * P;
-  ensure_workspace(m, B, H, W);
+  ensure_workspace(m, B, H, W, st);
   ada_model::PosCache& pc = get_pos(m, gh, gw);
   g_launches = 0;
   pdl_select(static_cast<long long>(M));
@@ -1243,8 +1375,7 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   }
   // output_conv1 -> bilinear to (H, W) -> output_conv2 (conv3x3 + ReLU + 1x1 + Sigmoid) (dpt.py:193-195)
   conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st);
-  static const int tail_mode = env_int("ADA_TAIL", 1);  // 1 = fused (tap GEMM at low res + gather), 0 = upsample + implicit GEMM
-  if (tail_mode == 1 && ph[1] * 14 == H * 8 && pw[1] * 14 == W * 8) {
+  if (tail_fused(ph[1], pw[1], H, W)) {
     GemmArgs e{};
     e.epi = EPI_BF16;
     e.out_bf16 = m->vtap;
@@ -1308,27 +1439,35 @@ static void forward_impl(ada_model* m, const float* rgb, const float* const* gui
   const size_t plane = static_cast<size_t>(B) * H * W * sizeof(float);
   if (m->graph_state == 1) {
     ADA_REQUIRE(n_guides >= 0 && n_guides <= 3, "at most 3 guide tensors");
-    if (!m->cap_stream) ADA_CHECK_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
-    ADA_CHECK_CUDA(cudaMalloc(&m->g_rgb, 3 * plane));
-    ADA_CHECK_CUDA(cudaMalloc(&m->g_out, plane));
-    m->g_nguides = n_guides;
-    for (int i = 0; i < n_guides; ++i) {
-      m->g_guide_ch[i] = guide_ch[i];
-      ADA_CHECK_CUDA(cudaMalloc(&m->g_guides[i], guide_ch[i] * plane));
-    }
-    // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
-    ADA_CHECK_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    // Any failure below (an allocation, the capture, the instantiation) releases everything acquired so far through
+    // drop_graph(), so a later call starts from a clean state instead of leaking the staging buffers.
+    bool capturing = false;
     try {
+      if (!m->cap_stream) ADA_CHECK_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+      ADA_CHECK_CUDA(cudaMalloc(&m->g_rgb, 3 * plane));
+      ADA_CHECK_CUDA(cudaMalloc(&m->g_out, plane));
+      m->g_nguides = n_guides;
+      for (int i = 0; i < n_guides; ++i) {
+        m->g_guide_ch[i] = guide_ch[i];
+        ADA_CHECK_CUDA(cudaMalloc(&m->g_guides[i], guide_ch[i] * plane));
+      }
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+      ADA_CHECK_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+      capturing = true;
       forward_body(m, m->g_rgb, m->g_guides, m->g_guide_ch, n_guides, m->g_out, B, H, W, m->cap_stream);
+      capturing = false;
+      ADA_CHECK_CUDA(cudaStreamEndCapture(m->cap_stream, &m->graph));
+      ADA_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
     } catch (...) {
-      cudaGraph_t dead = nullptr;
-      cudaStreamEndCapture(m->cap_stream, &dead);
-      if (dead) cudaGraphDestroy(dead);
+      if (capturing) {
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(m->cap_stream, &dead);
+        if (dead) cudaGraphDestroy(dead);
+      }
+      cudaGetLastError();
       m->drop_graph();
       throw;
     }
-    ADA_CHECK_CUDA(cudaStreamEndCapture(m->cap_stream, &m->graph));
-    ADA_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
     m->graph_state = 2;
   }
   ADA_REQUIRE(n_guides == m->g_nguides, "guide tensors differ from the captured call");
@@ -1372,8 +1511,12 @@ const char* ada_last_error(void) { return g_last_error.c_str(); }
 int ada_debug_timeline(long long* out, int32_t n) {
   return guarded([&] {
     ADA_REQUIRE(out && n > 0 && n <= 512, "bad argument");
+#ifdef ADA_BRINGUP
     ADA_CHECK_CUDA(cudaDeviceSynchronize());
     ADA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_dev_timeline, sizeof(long long) * n));
+#else
+    throw AdaError(ADA_ESTATE, "ada_debug_timeline: this library was built without -DADA_BRINGUP (no instrumented kernels)");
+#endif
   });
 }
 
@@ -1391,8 +1534,15 @@ int ada_create(const ada_config* cfg, ada_handle* out) {
     ADA_REQUIRE(cfg->sigmoid >= 0 && cfg->sigmoid <= 2, "sigmoid (final activation) in {0: none, 1: sigmoid, 2: relu}");
     ADA_REQUIRE((cfg->input_projection | 1) == 1 && (cfg->normalize_input | 1) == 1, "input_projection / normalize_input are flags");
     for (int i = 0; i < 4; ++i) ADA_REQUIRE(cfg->out_channels[i] % 8 == 0, "out_channels % 8");
+    ADA_REQUIRE(cfg->depth > 0 && cfg->depth <= 64 && cfg->ffn_hidden % 64 == 0 && cfg->pos_grid > 0, "bad depth / ffn_hidden / pos_grid");
+    ADA_REQUIRE(cfg->ffn_kind == 0 || cfg->ffn_kind == 1, "ffn_kind is 0 (Mlp) or 1 (SwiGLU)");
     ada_model* m = new ada_model();
     m->cfg = *cfg;
+    m->spec = expected_weights(*cfg);
+    if (cudaGetDevice(&m->device) != cudaSuccess) {  // no device: weights can still be staged, finalize / forward will fail
+      cudaGetLastError();
+      m->device = -1;
+    }
     *out = m;
   });
 }
@@ -1401,11 +1551,21 @@ int ada_set_weight(ada_handle h, const char* key, const float* data, const int64
   return guarded([&] {
     ADA_REQUIRE(h && key && data && shape && ndim >= 0 && ndim <= 8, "bad argument");
     if (h->finalized) throw AdaError(ADA_ESTATE, "ada_set_weight after ada_finalize");
+    auto sp = h->spec.find(key);
+    if (sp == h->spec.end())
+      throw AdaError(ADA_EINVAL, std::string("ada_set_weight: unknown weight key for this architecture: ") + key);
     HostTensor t;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) {
       t.shape.push_back(shape[i]);
       n *= static_cast<size_t>(shape[i]);
+    }
+    if (t.shape != sp->second) {
+      std::string msg = std::string("ada_set_weight: shape mismatch for ") + key + ": got [";
+      for (auto v : t.shape) msg += std::to_string(v) + ",";
+      msg += "] expected [";
+      for (auto v : sp->second) msg += std::to_string(v) + ",";
+      throw AdaError(ADA_EINVAL, msg + "]");
     }
     t.data.resize(n);
     cudaPointerAttributes attr;
@@ -1461,6 +1621,7 @@ int ada_set_graph(ada_handle h, int32_t on) {
 
 int ada_set_capture(ada_handle h, int32_t on) {
   if (!h) return ADA_EINVAL;
+  if (h->capture != (on != 0)) h->wsB = 0;  // the "tokens" copy is only planned while capturing: force a re-plan
   h->capture = on != 0;
   return ADA_OK;
 }

@@ -42,7 +42,8 @@ struct AttArgs {
   float scale_log2e;         // d^-0.5 * log2(e)
 };
 
-// VARIANT is a measurement knob (env ADA_ATT_VARIANT): 0 = product (6 of every 16 exponential pairs, evenly spaced, on the
+// VARIANT is a measurement knob of bring-up builds (-DADA_BRINGUP, env ADA_ATT_VARIANT; the product library instantiates
+// variant 0 only): 0 = product (6 of every 16 exponential pairs, evenly spaced, on the
 // FMA pipe), 1 = every exponential on MUFU, 3 = 6/16 clustered, 4 = 8/16, 5 = 4/16, 2 = exponentials replaced by a copy
 // (timing skeleton only, wrong results), 10 = clock64 timeline of one softmax thread and of the issuer thread.
 template <bool B>
@@ -132,10 +133,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       umma_commit_w(k_empty(s));
       umma_commit_w(s_full);
     };
+#ifdef ADA_BRINGUP
     const bool tli = (VARIANT == 10) && lane == 0 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
     auto istamp = [&](int j, int k) {
       if (tli) g_dev_timeline[128 + j * 8 + k] = clock64();
     };
+#else
+    auto istamp = [](int, int) {};
+#endif
     mbar_wait(q_full, 0, 0x530);
     issue_s(0);
     for (int j = 0; j < num_kv; ++j) {
@@ -167,10 +172,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     const float c = a.scale_log2e;
     float m_used = -INFINITY, l_part = 0.f;
 
+#ifdef ADA_BRINGUP
     const bool tl = (VARIANT == 10) && threadIdx.x == 64 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
     auto stamp = [&](int j, int k) {
       if (tl) g_dev_timeline[j * 8 + k] = clock64();
     };
+#else
+    auto stamp = [](int, int) {};
+#endif
     // One KV tile. MASKED is a compile-time tag: only the ragged last tile carries the 64 compare+select pairs that
     // overwrite the scores of keys past N (zero-filled by TMA) with -inf. As a run-time `if` inside a single loop body the
     // compiler if-converted them into ~130 always-executed instructions per tile (of ~450).

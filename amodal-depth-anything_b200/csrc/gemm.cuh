@@ -91,7 +91,7 @@ struct GemmArgs {
   int ks, cout;             // EPI_CONVT: kernel == stride, output channels
   int sigmoid;              // EPI_TAIL
   int has_relu_copy;        // EPI_BF16: also store relu(out) through tmap_c2
-  int debug_timeline;       // bring-up: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase into g_dev_timeline
+  int debug_timeline;       // bring-up builds (-DADA_BRINGUP) only: warp 4 lane 0 of CTA 0 stamps clock64 per epilogue phase
 };
 
 #ifndef ADA_RESID_BUFS
@@ -333,11 +333,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr bool stage_vec = tma_out || EPI == EPI_RESID_F32;  // bias / gamma staged in shared memory per N tile
     uint32_t xld_phase = 0;  // EPI_RESID_F32: phase bit per staging buffer (bits 0..2)
     int xbuf = 0;            // EPI_RESID_F32: staging buffer of the next block to consume
+#ifdef ADA_BRINGUP
     const bool tl = g.debug_timeline && blockIdx.x == 0 && warp == 4 && lane == 0;
     int tl_i = 0;
     auto stamp = [&](int k) {
       if (tl && tl_i < 60) g_dev_timeline[tl_i * 8 + k] = clock64();
     };
+#else
+    auto stamp = [](int) {};
+#endif
     for (int t = unit; t < num_tiles; t += num_units) {
       const int mt = t / tiles_n, nt = t % tiles_n;
       const int n0 = nt * BN;
@@ -648,7 +652,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       // accumulator stage drained -> hand it back to the MMA warp
       stamp(6);
+#ifdef ADA_BRINGUP
       ++tl_i;
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -12,8 +12,11 @@ namespace ada {
 // Device-side error mailbox: a kernel that times out on a barrier records why and traps, so a
 // protocol bug surfaces as a CUDA error with a reason instead of hanging the GPU.
 __device__ unsigned int g_dev_error[4];
-// Bring-up timeline buffer (clock64 stamps written by instrumented kernel variants, read through ada_debug_timeline).
+#ifdef ADA_BRINGUP
+// Bring-up timeline buffer (clock64 stamps written by instrumented kernel variants, read through ada_debug_timeline);
+// only bring-up builds (-DADA_BRINGUP) carry it and the stamping code.
 __device__ long long g_dev_timeline[512];
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

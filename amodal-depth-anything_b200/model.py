@@ -163,11 +163,15 @@ class _NativeModel(nn.Module):
             L.load().ada_destroy(self._handle)
             self._handle = None
 
-    def __del__(self):
-        try:
-            self._release()
-        except Exception:  # noqa: BLE001  interpreter shutdown
-            pass
+    # The C handle (a ctypes pointer to device-side packed weights) never travels with a copy of the module: copy.copy /
+    # copy.deepcopy / pickle / torch.save(model) get the parameters only and the copy lazily builds its own handle on its
+    # first forward -- as the reference nn.Module, which is freely copied for EMA or replica purposes.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"] = None
+        state["_handle_device"] = None
+        state["_dirty"] = True
+        return state
 
     def _ensure_handle(self, device):
         if self._handle is not None and not self._dirty and self._handle_device == device:

@@ -13,8 +13,16 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t=None):
+    """Current stream of the device the operands live on (not of whatever device happens to be current)."""
+    dev = t.device if t is not None else None
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _on(t):
+    """Context that makes `t`'s device current for the duration of a C-ABI call: the library launches on the current
+    device, so an operand on cuda:1 while cuda:0 is current must switch first."""
+    return torch.cuda.device(t.device)
 
 
 def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,
@@ -42,7 +50,7 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
         setattr(d, name, t.data_ptr() if t is not None else None)
     d.ldo, d.P, d.ks, d.cout, d.sigmoid, d.force_bn = ldo, P, ks, cout, sigmoid, force_bn
     d.force_cg = force_cg
-    L.check(lib.ada_op_gemm(ctypes.byref(d), _stream()))
+    _call(A, lib.ada_op_gemm, ctypes.byref(d))
 
 
 def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=False, delta2=None):
@@ -51,28 +59,28 @@ def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=Fa
         out = torch.empty((rows // n_tok) * (n_tok - 1), D, dtype=torch.bfloat16, device=x.device)
     else:
         out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
-    L.check(L.load().ada_op_layernorm(_p(x), _p(delta), _p(delta2), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls),
-                                      int(write_x), _stream()))
+    _call(x, L.load().ada_op_layernorm, _p(x), _p(delta), _p(delta2), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls),
+                                      int(write_x))
     return out
 
 
 def attention(qkv, B, N, heads):
     out = torch.empty(B * N, heads * 64, dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().ada_op_attention(_p(qkv), _p(out), B, N, heads, _stream()))
+    _call(qkv, L.load().ada_op_attention, _p(qkv), _p(out), B, N, heads)
     return out
 
 
 def channel_ln_relu(x_nhwc, w, b, eps=1e-6):
     C = x_nhwc.shape[-1]
     out = torch.empty_like(x_nhwc)
-    L.check(L.load().ada_op_channel_ln_relu(_p(x_nhwc), _p(w), _p(b), _p(out), x_nhwc.numel() // C, C, eps, _stream()))
+    _call(x_nhwc, L.load().ada_op_channel_ln_relu, _p(x_nhwc), _p(w), _p(b), _p(out), x_nhwc.numel() // C, C, eps)
     return out
 
 
 def upsample(x_nhwc, Ho, Wo):
     B, Hi, Wi, C = x_nhwc.shape
     out = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x_nhwc.device)
-    L.check(L.load().ada_op_upsample(_p(x_nhwc), _p(out), B, Hi, Wi, Ho, Wo, C, _stream()))
+    _call(x_nhwc, L.load().ada_op_upsample, _p(x_nhwc), _p(out), B, Hi, Wi, Ho, Wo, C)
     return out
 
 
@@ -82,7 +90,7 @@ def patch_gather(rgb, guides, Kpad):
     n = len(guides)
     ptrs = (ctypes.c_void_p * max(n, 1))(*[g.data_ptr() for g in guides])
     chs = (ctypes.c_int32 * max(n, 1))(*[g.shape[1] for g in guides])
-    L.check(L.load().ada_op_patch_gather(_p(rgb), ptrs, chs, n, _p(out), B, H, W, Kpad, _stream()))
+    _call(rgb, L.load().ada_op_patch_gather, _p(rgb), ptrs, chs, n, _p(out), B, H, W, Kpad)
     return out
 
 
@@ -90,7 +98,7 @@ def im2col_s2(x_nhwc):
     B, H, W, C = x_nhwc.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device=x_nhwc.device)
-    L.check(L.load().ada_op_im2col_s2(_p(x_nhwc), _p(out), B, H, W, C, _stream()))
+    _call(x_nhwc, L.load().ada_op_im2col_s2, _p(x_nhwc), _p(out), B, H, W, C)
     return out
 
 
@@ -126,7 +134,7 @@ def tail_gather(V, bias2, aux, H, W, sigmoid=True):
     """V: NHWC bf16 [B,Hl,Wl,288] -> fp32 [B,H,W]."""
     B, Hl, Wl, _ = V.shape
     out = torch.empty(B, H, W, dtype=torch.float32, device=V.device)
-    L.check(L.load().ada_op_tail_gather(_p(V), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, int(sigmoid), _stream()))
+    _call(V, L.load().ada_op_tail_gather, _p(V), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, int(sigmoid))
     return out
 
 
@@ -136,7 +144,7 @@ def image_nearest(img_u8_hwc, H=518, W=518, normalize=False):
     H0, W0, C = img_u8_hwc.shape
     assert C == 3 and img_u8_hwc.dtype == torch.uint8 and img_u8_hwc.is_contiguous()
     out = torch.empty(1, 3, H, W, dtype=torch.float32, device=img_u8_hwc.device)
-    L.check(L.load().ada_pre_image_nearest(_p(img_u8_hwc), H0, W0, _p(out), H, W, int(normalize), _stream()))
+    _call(img_u8_hwc, L.load().ada_pre_image_nearest, _p(img_u8_hwc), H0, W0, _p(out), H, W, int(normalize))
     return out
 
 
@@ -146,7 +154,7 @@ def mask_nearest(mask_u8, H=518, W=518):
     assert mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
     m01 = torch.empty(1, 1, H, W, dtype=torch.float32, device=mask_u8.device)
     guide = torch.empty_like(m01)
-    L.check(L.load().ada_pre_mask_nearest(_p(mask_u8), H0, W0, _p(m01), _p(guide), H, W, _stream()))
+    _call(mask_u8, L.load().ada_pre_mask_nearest, _p(mask_u8), H0, W0, _p(m01), _p(guide), H, W)
     return m01, guide
 
 
@@ -155,7 +163,7 @@ def minmax_normalize(depth):
     d = depth.contiguous()
     base, obs = torch.empty_like(d), torch.empty_like(d)
     scratch = torch.empty(2, dtype=torch.int32, device=d.device)
-    L.check(L.load().ada_post_minmax_normalize(_p(d), d.numel(), _p(base), _p(obs), _p(scratch), _stream()))
+    _call(d, L.load().ada_post_minmax_normalize, _p(d), d.numel(), _p(base), _p(obs), _p(scratch))
     return base, obs
 
 
@@ -163,8 +171,7 @@ def blend_seam(raw01, amodal, mask01):
     """infer.py:30-44 median_filter_blend(amodal, raw, mask, 3) on [H,W] fp32 device maps."""
     H, W = raw01.shape[-2:]
     out = torch.empty(H, W, dtype=torch.float32, device=raw01.device)
-    L.check(L.load().ada_post_blend_seam(_p(raw01.contiguous()), _p(amodal.contiguous()), _p(mask01.contiguous()), _p(out), H, W,
-                                         _stream()))
+    _call(raw01, L.load().ada_post_blend_seam, _p(raw01.contiguous()), _p(amodal.contiguous()), _p(mask01.contiguous()), _p(out), H, W)
     return out
 
 
@@ -182,8 +189,8 @@ def eval_sample(pred, depth_gt, depth_obs, visible_mask, object_mask):
     scratch = torch.empty(26, dtype=torch.float64, device=pred.device)
     vis = visible_mask.to(torch.uint8).contiguous()
     obj = object_mask.to(torch.uint8).contiguous()
-    L.check(L.load().ada_eval_sample(_p(pred.contiguous()), h, w, _p(depth_gt.contiguous()), _p(depth_obs.contiguous()), _p(vis),
-                                     _p(obj), H, W, _p(out), _p(scratch), _stream()))
+    _call(pred, L.load().ada_eval_sample, _p(pred.contiguous()), h, w, _p(depth_gt.contiguous()), _p(depth_obs.contiguous()), _p(vis),
+                                     _p(obj), H, W, _p(out), _p(scratch))
     return out
 
 

@@ -51,17 +51,24 @@ typedef struct ada_config {
 /* ---- model lifetime -------------------------------------------------------------------------------------------- */
 /* Replaces AmodalDAv2.__init__ / DepthAnythingV2.__init__ (dav2.py:22-61, dpt.py:201-223): creates an empty model. */
 int ada_create(const ada_config* cfg, ada_handle* out);
-/* Replaces nn.Module.load_state_dict for one tensor: `key` is the reference state-dict name relative to
+/* Replaces nn.Module.load_state_dict(strict=True) for one tensor: `key` is the reference state-dict name relative to
  * `encoder.` (e.g. "pretrained.blocks.3.attn.qkv.weight", "depth_head.scratch.layer1_rn.weight"); data is fp32,
- * contiguous, host or device memory (copied; the caller keeps ownership). Shapes are checked against the config. */
+ * contiguous, host or device memory (copied; the caller keeps ownership). A key that is not part of the architecture
+ * described by the config, or a shape that differs from the reference's, fails with ADA_EINVAL (nothing is stored). */
 int ada_set_weight(ada_handle h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
 /* Packs weights for the kernels: bf16 K-major GEMM operands, fused (3+Cg)-channel patch-embed weight, tap-major conv
- * weights, pre-added biases. Fails with ADA_ESTATE and lists missing keys if the state dict is incomplete. */
+ * weights, pre-added biases. Fails with ADA_ESTATE if the state dict is incomplete; ada_last_error() then names every
+ * missing key (up to 24 of them, with the total count). */
 int ada_finalize(ada_handle h);
 /* Replaces AmodalDAv2.forward (dav2.py:64-85) in eval mode. rgb: [B,3,H,W] fp32 in [0,1] (ImageNet normalisation is
  * applied inside, dav2.py:65). guides[i]: [B,guide_ch[i],H,W] fp32, concatenated in order along channels (dav2.py:67-76);
  * sum(guide_ch) must equal cfg.guide_channels. out: [B,1,H,W] fp32. All device pointers, NCHW contiguous.
- * H and W must be multiples of 14 (patch_embed.py:73-74). Asynchronous on `stream` (a cudaStream_t); no host sync. */
+ * H and W must be multiples of 14 (patch_embed.py:73-74). Asynchronous on `stream` (a cudaStream_t). The call performs no
+ * host synchronisation EXCEPT the first time a handle sees a new (B,H,W): the workspace is then re-planned, which drains
+ * `stream` first (earlier forwards of this handle may still use the old layout) and may cudaMalloc; the position table of a
+ * new patch grid is interpolated on the host once and cached. Steady-state calls at a seen shape are fully asynchronous.
+ * Threading: a handle belongs to the device that was current at ada_create and is driven from one thread and one stream
+ * at a time (not re-entrant); different handles -- also on different devices of one process -- are independent. */
 int ada_forward(ada_handle h, const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
                 float* out, int32_t B, int32_t H, int32_t W, void* stream);
 /* Bytes of device workspace the handle holds for its largest (B,H,W) so far. */
@@ -81,7 +88,8 @@ int ada_set_graph(ada_handle h, int32_t on);
 /* Measurement hook (bench.py): when on, every kernel launch of ada_forward is bracketed by CUDA events on the launch
  * stream. ada_profile_read syncs, then sums per kernel class since the last read: elapsed ms, algorithmic FLOPs,
  * algorithmic bytes, launches. Classes: 0 tcgen05 GEMM (linear), 1 tcgen05 GEMM (implicit conv3x3), 2 attention,
- * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls / im2col). n_classes >= 7. */
+ * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls / im2col), 7 fused tail
+ * gather. n_classes >= 8. */
 int ada_set_profile(ada_handle h, int32_t on);
 int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches);
 /* Raw records since the last ada_profile_read (call before it): meta[5*i..] = class, M, N, K, epi|act<<4|BN<<8; ms[i].
@@ -91,7 +99,9 @@ void ada_destroy(ada_handle h);
 const char* ada_last_error(void);
 /* Device error mailbox written by a kernel that timed out on a barrier (4 words: code, block, parity, thread). */
 int ada_device_error(uint32_t out[4]);
-/* Bring-up hook: clock64 stamps written by instrumented kernel variants (e.g. ADA_ATT_VARIANT=10); n <= 512. */
+/* Bring-up hook: clock64 stamps written by instrumented kernel variants; n <= 512. Only libraries built with
+ * -DADA_BRINGUP carry the instrumented kernels (and the ADA_ATT_VARIANT / ADA_GEMM_TIMELINE knobs); the product build
+ * returns ADA_ESTATE here. */
 int ada_debug_timeline(long long* out, int32_t n);
 
 /* ---- host utility (runs on the CPU; no device needed) -------------------------------------------------------- */

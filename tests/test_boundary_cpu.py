@@ -126,3 +126,104 @@ def test_unguided_model_mirrors_reference_class():
     for hw, want_hw in (((480, 640), (518, 686)), ((1000, 518), (994, 518)), ((300, 900), (518, 1554)),
                         ((777, 333), (1204, 518)), ((1080, 1920), (518, 924))):
         assert pkg.DepthAnythingV2._input_size(*hw) == want_hw
+
+
+def _tiny_cfg():
+    cfg = L.AdaConfig()
+    cfg.embed_dim, cfg.depth, cfg.num_heads, cfg.ffn_kind, cfg.ffn_hidden = 384, 12, 6, 0, 1536
+    cfg.taps = (ctypes.c_int32 * 4)(2, 5, 8, 11)
+    cfg.features = 64
+    cfg.out_channels = (ctypes.c_int32 * 4)(48, 96, 192, 384)
+    cfg.guide_channels, cfg.sigmoid, cfg.pos_grid, cfg.interpolate_offset = 2, 1, 37, 0.1
+    cfg.input_projection, cfg.normalize_input = 1, 1
+    return cfg
+
+
+def test_set_weight_is_strict_and_finalize_lists_missing_keys():
+    """ABI contract of include/amodal_b200.h (== load_state_dict(strict=True)): unknown keys and wrong shapes are rejected
+    with ADA_EINVAL, an incomplete state dict fails ada_finalize with ADA_ESTATE naming the missing tensors. Host-only:
+    no kernel is launched, so this runs on the build box."""
+    lib = L.load()
+    h = ctypes.c_void_p()
+    assert lib.ada_create(ctypes.byref(_tiny_cfg()), ctypes.byref(h)) == 0
+    try:
+        w = torch.zeros(384)
+        shp = (ctypes.c_int64 * 1)(384)
+        assert lib.ada_set_weight(h, b"pretrained.norm.weight", ctypes.c_void_p(w.data_ptr()), shp, 1) == 0
+        rc = lib.ada_set_weight(h, b"pretrained.norm.wieght", ctypes.c_void_p(w.data_ptr()), shp, 1)
+        assert rc == L.ADA_EINVAL and b"unknown weight key" in lib.ada_last_error()
+        rc = lib.ada_set_weight(h, b"pretrained.blocks.12.norm1.weight", ctypes.c_void_p(w.data_ptr()), shp, 1)  # depth is 12
+        assert rc == L.ADA_EINVAL
+        bad = (ctypes.c_int64 * 1)(383)
+        rc = lib.ada_set_weight(h, b"pretrained.norm.bias", ctypes.c_void_p(w.data_ptr()), bad, 1)
+        assert rc == L.ADA_EINVAL and b"shape mismatch" in lib.ada_last_error()
+        rc = lib.ada_finalize(h)
+        assert rc == L.ADA_ESTATE
+        msg = lib.ada_last_error().decode()
+        n_expected = len(synth.state_dict_shapes("vits", "mask+observation"))
+        assert f"{n_expected - 1} of {n_expected} tensors were never set" in msg, msg
+        assert "depth_head.projects.0.bias" in msg and "pretrained.norm.weight" not in msg
+    finally:
+        lib.ada_destroy(h)
+
+
+def _cfg_for(enc, gt, ip):
+    c = pkg.MODEL_CONFIGS[enc]
+    cfg = L.AdaConfig()
+    cfg.embed_dim, cfg.depth, cfg.num_heads = c["embed_dim"], c["depth"], c["num_heads"]
+    cfg.ffn_kind, cfg.ffn_hidden = (0 if c["ffn"] == "mlp" else 1), c["hidden"]
+    cfg.taps = (ctypes.c_int32 * 4)(*c["taps"])
+    cfg.features = c["features"]
+    cfg.out_channels = (ctypes.c_int32 * 4)(*c["out_channels"])
+    cfg.guide_channels, cfg.sigmoid, cfg.pos_grid, cfg.interpolate_offset = pkg.GUIDE_CHANNELS[gt], 1, 37, 0.1
+    cfg.input_projection, cfg.normalize_input = int(ip), 1
+    return cfg
+
+
+@pytest.mark.parametrize("enc,gt,ip", [("vits", "mask+observation", True), ("vitb", "none", False),
+                                       ("vitg", "image+mask+observation", True)])
+def test_expected_weight_table_equals_reference_state_dict(enc, gt, ip):
+    """The library's own table of expected tensors (csrc/ada_api.cu expected_weights) equals the reference state dict for
+    guided / un-guided heads and the Mlp / SwiGLU encoders: every reference key is known with the reference shape, and a
+    complete state dict leaves nothing missing (finalize then only fails for want of a device on the build box)."""
+    lib = L.load()
+    h = ctypes.c_void_p()
+    assert lib.ada_create(ctypes.byref(_cfg_for(enc, gt, ip)), ctypes.byref(h)) == 0
+    full = enc != "vitg"  # ViT-G: 5.4 GB of fp32 -- probe keys and shapes without staging the data
+    try:
+        dummy = torch.zeros(4)
+        for k, shp in synth.state_dict_shapes(enc, gt, input_projection=ip).items():
+            key = k[len("encoder."):].encode()
+            if full:
+                t = torch.zeros(shp)
+                arr = (ctypes.c_int64 * len(shp))(*shp)
+                assert lib.ada_set_weight(h, key, ctypes.c_void_p(t.data_ptr()), arr, len(shp)) == 0, (k, lib.ada_last_error())
+            else:  # a wrong shape is refused before any byte is read; the message carries the expected shape
+                arr = (ctypes.c_int64 * 1)(3)
+                assert lib.ada_set_weight(h, key, ctypes.c_void_p(dummy.data_ptr()), arr, 1) == L.ADA_EINVAL
+                msg = lib.ada_last_error().decode()
+                assert "shape mismatch" in msg and "expected [" + "".join(f"{v}," for v in shp) + "]" in msg, (k, msg)
+        if full:
+            assert lib.ada_finalize(h) in (0, L.ADA_ENODEVICE), lib.ada_last_error()
+    finally:
+        lib.ada_destroy(h)
+
+
+def test_model_copies_do_not_share_the_native_handle():
+    """copy / deepcopy / pickle of the module (EMA copies, torch.save(model)) carry parameters only; the ctypes handle is
+    dropped and rebuilt lazily by the copy (a shared handle would be destroyed twice)."""
+    import copy
+    import io
+    m = pkg.AmodalDAv2(guide_type="mask", encoder="vits", pretrained=False)
+    m._handle, m._handle_device, m._dirty = ctypes.c_void_p(1234), torch.device("cpu"), False  # stand-in for a live handle
+    try:
+        for c in (copy.copy(m), copy.deepcopy(m)):
+            assert c._handle is None and c._dirty and c._handle_device is None
+            assert torch.equal(c.state_dict()["encoder.pretrained.pos_embed"], m.state_dict()["encoder.pretrained.pos_embed"])
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        m2 = torch.load(buf, weights_only=False)
+        assert m2._handle is None and m2._dirty
+    finally:
+        m._handle = None
