@@ -4,9 +4,14 @@
   torchrun ... bench.py --gpus N --steps K --warmup W        # N ranks, images sharded, no data-path collective
   python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host CPU cores (oracle port)
 
-A step = one forward pass over one synthetic batch (ViT-L, 518x518, guide = mask+observation, 32 images per GPU).
-`value` is device-timed (CUDA events on the launch stream, inputs resident in HBM); `e2e` goes through the public model
-API with pinned host buffers, H2D and D2H inside the timed region. Prints ONE JSON line on rank 0.
+A step = one forward pass over one synthetic batch. Default workload = BASELINE.json configs[2]: ViT-L, 518x518, guide =
+mask+observation, 32 images per GPU (weak scaling; with N > 1 the same JSON line also carries `strong` = the configuration
+as BASELINE words it, global batch 32 sharded over the N GPUs). `value` is device-timed (CUDA events on the launch stream,
+inputs resident in HBM); `e2e` goes through the public model API with pinned host buffers, H2D and D2H inside the timed
+region. Outside the timed regions the same run also: checks one image of the timed output against the CPU oracle
+(`parity`), times the reference algorithm with stock torch kernels on the same GPU (`gpu_eager_baseline`: fp32 without
+TF32, and bf16 autocast -- the "kernel to beat" on this box) and on the host cores (`cpu_baseline`), and measures the other
+BASELINE configurations (`other_configs`). Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -24,7 +29,11 @@ sys.path.insert(0, ROOT)
 GFLOP_PER_IMAGE = {("vits", 518): 119.4, ("vitb", 518): 396.3, ("vitl", 518): 1389.6, ("vitl", 1036): 7764.3,
                    ("vitg", 518): 5771.4}
 PROF_CLASSES = ["gemm_tcgen05_linear", "gemm_tcgen05_conv3x3", "attention_tcgen05", "layernorm", "channel_ln_relu",
-                "upsample_bilinear", "gather"]
+                "upsample_bilinear", "gather", "tail_gather"]
+# BASELINE.json `configs`, by (encoder, size, per-GPU batch)
+BASELINE_CONFIGS = {("vits", 518, 1): "configs[0]", ("vitb", 518, 8): "configs[1]", ("vitl", 518, 32): "configs[2]",
+                    ("vitl", 1036, 4): "configs[3]", ("vitg", 518, 8): "configs[4] (per-GPU share of batch 64 over 8 GPUs)"}
+GT = "mask+observation"
 
 
 def load_peaks():
@@ -85,19 +94,19 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ CPU / reference legs
 def cpu_reference_rate(encoder, size, steps, warmup):
-    """Times the oracle (CPU restatement of the reference forward) on all host cores: `steps` images, one per step."""
+    """Times the oracle (CPU restatement of the reference forward) on all host cores: `steps` images, ONE image per step."""
     import torch
     from oracle import amodal_oracle as O
     from oracle import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    gt = "mask+observation"
-    sd = synth.make_state_dict(encoder, gt, 0)
+    sd = synth.make_state_dict(encoder, GT, 0)
     inp = synth.make_inputs(1, size, size, 0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward(sd, encoder, gt, inp["x"], None, inp["guide_mask"], inp["observation"])
+        O.forward(sd, encoder, GT, inp["x"], None, inp["guide_mask"], inp["observation"])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
@@ -119,16 +128,22 @@ def cpu_context():
 
 
 def run_reference(a):
+    """Reference arm: the reference algorithm (oracle port; the reference is pure Python and /root/reference does not exist
+    on the GPU box) on the host CPU cores. A step here is ONE image of the named architecture and resolution -- a bounded
+    sample of the workload (a 32-image CPU step would take ~30 s); images/s is batch-size independent on the CPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rate, sec, cores = cpu_reference_rate(a.encoder, a.size, a.steps, a.warmup)
-    sample = f"{a.steps} steps x 1 image ({a.encoder} {a.size}x{a.size}, fp32, torch CPU) after {a.warmup} warm-up"
+    sample = (f"{a.steps} steps x 1 image per step ({a.encoder} {a.size}x{a.size}, fp32, torch CPU, {cores} threads) after "
+              f"{a.warmup} warm-up; NOT the {a.batch}-image step of the GPU arm")
+    cfg = workload_config(a, a.gpus)
+    cfg["reference_step"] = "1 image per step (bounded CPU sample of the same architecture and resolution)"
     line = {
         "impl": "reference", "metric": "images/sec", "value": rate, "unit": "images/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, a.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -136,21 +151,131 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, world):
-    per_gpu = a.batch if a.scaling == "weak" else max(a.batch // world, 1)
-    in_mb = per_gpu * 5 * a.size * a.size * 4 / 1e6
-    # fp32 residual stream alone: tokens x D x 4 B, rewritten every block
-    d = {"vits": 384, "vitb": 768, "vitl": 1024, "vitg": 1536}[a.encoder]
-    x_mb = per_gpu * ((a.size // 14) ** 2 + 1) * d * 4 / 1e6
+def workload_config(a, world, per_gpu=None, encoder=None, size=None):
+    encoder, size = encoder or a.encoder, size or a.size
+    if per_gpu is None:
+        per_gpu = a.batch if a.scaling == "weak" else max(a.batch // world, 1)
+    in_mb = per_gpu * 5 * size * size * 4 / 1e6
+    d = {"vits": 384, "vitb": 768, "vitl": 1024, "vitg": 1536}[encoder]
+    x_mb = per_gpu * ((size // 14) ** 2 + 1) * d * 4 / 1e6  # fp32 residual stream alone, rewritten every block
     l2 = (f"per step {in_mb:.0f} MB of inputs and a {x_mb:.0f} MB fp32 token stream (plus GBs of bf16 activations) stream through "
           f"the 126 MB L2" if in_mb + x_mb > 126 else
           f"small-batch configuration: inputs ({in_mb:.0f} MB) and token stream ({x_mb:.0f} MB) fit the 126 MB L2 and are NOT "
           f"flushed between steps -- latency figure, not the headline metric")
-    return {"workload": f"AmodalDAv2 {a.encoder} {a.size}x{a.size} guide=mask+observation forward, batch {per_gpu}/GPU "
-                        f"(BASELINE.json configs[2])",
-            "encoder": a.encoder, "height": a.size, "width": a.size, "per_gpu_batch": per_gpu,
+    tag = BASELINE_CONFIGS.get((encoder, size, per_gpu))
+    return {"workload": f"AmodalDAv2 {encoder} {size}x{size} guide=mask+observation forward, batch {per_gpu}/GPU"
+                        + (f" (BASELINE.json {tag})" if tag else " (not a BASELINE.json configuration)"),
+            "encoder": encoder, "height": size, "width": size, "per_gpu_batch": per_gpu,
             "global_batch": per_gpu * world, "parallelism": f"image-sharded x{world}, weights replicated, no collective",
             "cuda_graph": bool(getattr(a, "graph", False)), "l2": l2}
+
+
+# ------------------------------------------------------------------------------------------------ GPU helpers
+def make_model(pkg, torch, encoder, dev):
+    """Random-init weights of the named architecture (no checkpoints offline). The guidance conv is zero-initialised by the
+    reference (dav2.py:55-61) -- randomise it so the guide path does real work."""
+    torch.manual_seed(0)
+    model = pkg.AmodalDAv2(guide_type=GT, encoder=encoder, pretrained=False)
+    with torch.no_grad():
+        model.encoder.pretrained.patch_embed_guidance.proj.weight.normal_(std=0.02)
+        model.encoder.pretrained.patch_embed_guidance.proj.bias.uniform_(-0.05, 0.05)
+    return model.to(dev).eval()
+
+
+def make_inputs(torch, B, H, W, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.rand(B, 3, H, W, device=dev, generator=g)
+    low = torch.rand(B, 1, max(H // 37, 2), max(W // 37, 2), device=dev, generator=g)
+    mask = (torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear") > 0.5).float() * 2 - 1
+    obs = torch.rand(B, 1, H, W, device=dev, generator=g) * 2 - 1
+    return x, mask, obs
+
+
+def timed_loop(torch, fn, steps, warmup, barrier):
+    """W untimed calls, then K calls between two CUDA events on the current stream, barrier + synchronize on both sides."""
+    out = None
+    for _ in range(warmup):
+        out = fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def parity_check(torch, model, x, mask, obs, out, idx=0):
+    """One image of the timed output against the CPU oracle on the same weights / inputs (outside every timed region)."""
+    from oracle import amodal_oracle as O
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    xi, mi, oi = x[idx:idx + 1].cpu(), mask[idx:idx + 1].cpu(), obs[idx:idx + 1].cpu()
+    t0 = time.perf_counter()
+    ref = O.forward(sd, model.encoder_name, GT, xi, None, mi, oi)
+    sec = time.perf_counter() - t0
+    got = out[idx:idx + 1].detach().float().cpu()
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+    absrel = O.abs_relative_difference(got.clone(), ref, mi > 0).item()
+    return {"image": idx, "rel": rel, "absrel": absrel, "rel_tol": 1e-2, "absrel_tol": 1e-3,
+            "ok": bool(rel <= 1e-2 and absrel <= 1e-3), "oracle_s": sec,
+            "how": "max per-pixel |out-ref|/ref and AbsRel over the mask of one image of the timed batch vs oracle/amodal_oracle.py "
+                   "(fp32, CPU) on the same weights and inputs"}
+
+
+def gpu_eager_baseline(torch, model, x, mask, obs, steps=3, warmup=2):
+    """The reference algorithm with stock torch kernels (cuBLAS / cuDNN / ATen eager, materialised softmax(QK^T)V as in
+    attention.py:49-62) on the SAME GPU and the same batch: fp32 with TF32 off (the precision the reference runs in) and
+    torch.autocast(bfloat16). This is the same-box 'kernel to beat' (SURVEY.md section 8d); none of this repo's kernels run here."""
+    from oracle import amodal_oracle as O
+    res = {"native": "torch eager: cuBLAS / cuBLASLt GEMMs, cuDNN convolutions, ATen softmax / layer_norm / interpolate",
+           "torch": torch.__version__, "batch": int(x.shape[0]), "steps": steps, "warmup": warmup}
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        def run():
+            return O.forward(sd, model.encoder_name, GT, x, None, mask, obs)
+        for name, ctx in (("fp32_no_tf32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            try:
+                def fn():
+                    if ctx is None:
+                        return run()
+                    with ctx:
+                        return run()
+                ms, _ = timed_loop(torch, fn, steps, warmup, torch.cuda.synchronize)
+                res[name] = {"ms_per_step": ms, "images_per_s": x.shape[0] / (ms / 1e3)}
+            except Exception as e:  # noqa: BLE001  (e.g. out of memory at an unusual --batch)
+                res[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return res
+
+
+def measure_config(torch, pkg, dev, encoder, size, batch, steps, warmup, peaks, model=None):
+    """Device-timed images/s of one more BASELINE configuration (same kernels, same timing rules)."""
+    own = model is None
+    if own:
+        model = make_model(pkg, torch, encoder, dev)
+    x, mask, obs = make_inputs(torch, batch, size, size, dev, 4321)
+    ms, out = timed_loop(torch, lambda: model(x, guide_rgb=None, guide_mask=mask, observation=obs), steps, warmup,
+                         torch.cuda.synchronize)
+    ok = bool(torch.isfinite(out).all().item())
+    rate = batch / (ms / 1e3)
+    gf = GFLOP_PER_IMAGE.get((encoder, size))
+    r = {"workload": f"{encoder} {size}x{size} batch {batch}", "baseline_config": BASELINE_CONFIGS.get((encoder, size, batch)),
+         "value": rate, "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "finite": ok,
+         "gpu_launches_per_step": model.launch_count(),
+         "model_tflops": rate * gf / 1e3 if gf else None,
+         "frac_of_sustained_peak": rate * gf / 1e3 / peaks["tf_sustained"] if gf else None,
+         "frac_of_burst_peak": rate * gf / 1e3 / peaks["tf_burst"] if gf else None}
+    del x, mask, obs, out
+    if own:
+        del model
+    torch.cuda.empty_cache()
+    return r
 
 
 def main():
@@ -164,6 +289,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak) / total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip parity / gpu_eager_baseline / other_configs / strong (profiling runs under ncu)")
     ap.add_argument("--graph", action="store_true", help="replay the forward as a CUDA graph (launch-bound small batches)")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--detail", default="", help="write per-launch-signature timings of the profile pass to this JSON file")
@@ -188,23 +315,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_config(a, world)
     B, H, W = cfg["per_gpu_batch"], a.size, a.size
+    peaks = load_peaks()
 
-    # random-init weights of the named architecture (no checkpoints offline); the guidance conv is zero-initialised by the
-    # reference (dav2.py:55-61) -- randomise it so the guide path does real work
-    torch.manual_seed(0)
-    model = pkg.AmodalDAv2(guide_type="mask+observation", encoder=a.encoder, pretrained=False)
-    with torch.no_grad():
-        model.encoder.pretrained.patch_embed_guidance.proj.weight.normal_(std=0.02)
-        model.encoder.pretrained.patch_embed_guidance.proj.bias.uniform_(-0.05, 0.05)
-    model = model.to(dev).eval()
+    model = make_model(pkg, torch, a.encoder, dev)
     if a.graph:
         model.set_graph(True)
-
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.rand(B, 3, H, W, device=dev, generator=g)
-    low = torch.rand(B, 1, H // 37, W // 37, device=dev, generator=g)
-    mask = (torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear") > 0.5).float() * 2 - 1
-    obs = torch.rand(B, 1, H, W, device=dev, generator=g) * 2 - 1
+    x, mask, obs = make_inputs(torch, B, H, W, dev, 1234 + rank)
 
     def step():
         return model(x, guide_rgb=None, guide_mask=mask, observation=obs)
@@ -220,14 +336,7 @@ def main():
     sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(a.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / a.steps
+    ms, out = timed_loop(torch, step, a.steps, 0, barrier)
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ms, dev)
     launches = model.launch_count()
@@ -243,11 +352,12 @@ def main():
 
     def e2e_run(n):
         # every step: H2D of that step's pinned inputs, forward through the public model call, D2H of its result;
-        # copies of neighbouring steps overlap the kernels (copy stream), all inside the timed region
+        # copies of neighbouring steps overlap the kernels (copy streams), all inside the timed region
         runner.run(((hx, hm, ho) for _ in range(n)), [houts[i & 1] for i in range(n)])
 
     e2e_run(2)
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_run(a.steps)
     e1.record()
@@ -255,13 +365,31 @@ def main():
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / a.steps, dev)
     h2d = (hx.numel() + hm.numel() + ho.numel()) * 4
     d2h = hout.numel() * 4
+    e2e_same = bool(torch.equal(houts[(a.steps - 1) & 1], out.cpu()))  # the streamed path returns the same numbers
+
+    # ---- strong scaling as BASELINE words configs[2]: the GLOBAL batch (default 32) sharded over the N GPUs
+    strong = None
+    if world > 1 and a.scaling == "weak" and not a.no_extras:
+        per = max(a.batch // world, 1)
+        tokens = per * ((H // 14) * (W // 14) + 1)
+        sx, sm_, so = make_inputs(torch, per, H, W, dev, 99 + rank)
+        use_graph = tokens <= 12000  # launch-bound share: CUDA-graph replay (PDL is automatic below 12000 tokens)
+        model.set_graph(use_graph)
+        s_ms, s_out = timed_loop(torch, lambda: model(sx, guide_rgb=None, guide_mask=sm_, observation=so), a.steps,
+                                 max(a.warmup, 4), barrier)
+        s_ms = max_over_ranks(s_ms, dev)
+        model.set_graph(a.graph)
+        strong = {"scaling": "strong", "global_batch": per * world, "per_gpu_batch": per, "ms_per_step": s_ms,
+                  "value": per * world / (s_ms / 1e3), "unit": "images/s", "cuda_graph": use_graph,
+                  "finite": bool(torch.isfinite(s_out).all().item()),
+                  "note": "BASELINE.json configs[2] as worded: batch 32 sharded at N GPUs; device-timed, max over ranks"}
+        del sx, sm_, so, s_out
 
     # ---- per-kernel-class CUDA-event breakdown (separate pass: the events add gaps, so it is not the headline number)
     import ctypes
     from amodal_depth_anything_b200 import _lib as L
     lib = L.load()
     breakdown, roof = {}, None
-    peaks = load_peaks()
     if a.profile_steps > 0:
         lib.ada_set_profile(model._handle, 1)
         for _ in range(a.profile_steps):
@@ -293,34 +421,62 @@ def main():
         tot = sum(msv) or 1.0
         for i, name in enumerate(PROF_CLASSES):
             if ln[i]:
-                breakdown[name] = {"ms_per_step": msv[i] / a.profile_steps, "share": msv[i] / tot,
-                                   "launches_per_step": ln[i] // a.profile_steps,
-                                   "tflops": fl[i] / msv[i] / 1e9 if fl[i] else None,
-                                   "gbs": by[i] / msv[i] / 1e6 if not fl[i] else None}
+                e = {"ms_per_step": msv[i] / a.profile_steps, "share": msv[i] / tot,
+                     "launches_per_step": ln[i] // a.profile_steps}
+                if fl[i]:   # tensor-bound classes: algorithmic FLOP rate against the measured bf16 peaks
+                    e["tflops"] = fl[i] / msv[i] / 1e9
+                    e["frac_of_sustained_peak"] = e["tflops"] / peaks["tf_sustained"]
+                    e["frac_of_burst_peak"] = e["tflops"] / peaks["tf_burst"]
+                else:       # HBM-bound classes: algorithmic bytes against the measured copy bandwidth
+                    e["gbs"] = by[i] / msv[i] / 1e6
+                    e["frac_of_hbm_peak"] = e["gbs"] / peaks["hbm"]
+                breakdown[name] = e
         # dominant kernel = gemm_tcgen05_kernel (linear + implicit-conv launches of the same kernel)
         g_ms, g_fl, g_n = msv[0] + msv[1], fl[0] + fl[1], ln[0] + ln[1]
         ach = g_fl / g_ms / 1e9
         traffic, traffic_note = None, None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (never measured live)
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")))
-            if (a.encoder, a.size, a.batch) == ("vitl", 518, 32):
-                traffic = tj["mean_dram_bytes_per_launch"]
-                traffic_note = (f"mean over the 4 linear GEMMs of one encoder block (96 of {g_n // a.profile_steps} GEMM launches/"
-                                f"step), algorithmic {tj['mean_algorithmic_bytes_per_launch']} B/launch; {tj['source']}")
+        try:  # DRAM bytes per launch: STATIC, from the committed `ncu --set full` capture of this command (ncu cannot run inside bench.py)
+            for tf in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+                tp = os.path.join(ROOT, "profiles", tf)
+                if os.path.exists(tp) and (a.encoder, a.size, a.batch) == ("vitl", 518, 32):
+                    tj = json.load(open(tp))
+                    traffic = tj["mean_dram_bytes_per_launch"]
+                    traffic_note = (f"STATIC value read from profiles/{tf} (ncu --set full capture of this workload, not measured in "
+                                    f"this run): mean over the 4 linear GEMMs of one encoder block, algorithmic "
+                                    f"{tj['mean_algorithmic_bytes_per_launch']} B/launch; {tj['source']}")
+                    break
         except Exception:  # noqa: BLE001
             pass
         roof = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
-                "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "frac_of_burst": ach / peaks["tf_burst"],
+                "peak_burst": peaks["tf_burst"], "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peaks["src"] + ": `peak`/`frac` use the sustained bf16 figure (kernel timed inside a long step); "
+                                              "`frac_of_burst` uses the burst figure",
                 "flops_per_launch": g_fl / g_n, "avg_launch_ms": g_ms / g_n, "launches_per_step": g_n // a.profile_steps,
                 "share_of_step": g_ms / tot}
 
+    extras = rank == 0 and world == 1 and not a.no_extras
+    parity = eager = None
+    other = []
+    if rank == 0 and not a.no_extras:
+        parity = parity_check(torch, model, x, mask, obs, out)
+    if extras:
+        eager = gpu_eager_baseline(torch, model, x, mask, obs)
+        if (a.encoder, a.size, a.batch) == ("vitl", 518, 32):
+            # the other BASELINE.json configurations, same kernels and timing rules (ViT-L 1036^2 reuses the loaded weights)
+            other.append(measure_config(torch, pkg, dev, "vitl", 1036, 4, 5, 3, peaks, model=model))
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, sec, cores = cpu_reference_rate(a.encoder, a.size, 3, 1)
         cpu_base = {"context": cpu_context(), "value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": f"3 images of the same workload ({a.encoder} {a.size}x{a.size}, batch 1 per step, fp32 torch CPU "
+                    "sample": f"3 images of the same workload ({a.encoder} {a.size}x{a.size}, ONE image per step, fp32 torch CPU "
                               f"oracle) after 1 warm-up, {sec:.2f} s/image"}
+    workspace_gb = model.workspace_bytes() / 2 ** 30
+    if extras and (a.encoder, a.size, a.batch) == ("vitl", 518, 32):
+        del model, runner
+        torch.cuda.empty_cache()
+        other.append(measure_config(torch, pkg, dev, "vitb", 518, 8, 10, 3, peaks))
+        other.append(measure_config(torch, pkg, dev, "vitg", 518, 8, 5, 3, peaks))
 
     if rank == 0:
         gb = cfg["global_batch"]
@@ -331,18 +487,26 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": cfg,
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
-                    "how": "StreamedInference: pinned host -> H2D -> AmodalDAv2.forward -> D2H per step, copies on a side stream"},
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms, "same_result_as_device_timed_call": e2e_same,
+                    "how": "StreamedInference: pinned host -> H2D -> AmodalDAv2.forward -> D2H per step, copies on side streams"},
             "gpu_launches": launches * a.steps,
             "clocks": clocks,
             "roofline": roof,
+            "parity": parity,
             "model_tflops_per_gpu": value * gf / 1e3 / world if gf else None,
             "model_frac_of_peak": (value * gf / 1e3 / world) / peaks["tf_sustained"] if gf else None,
             "model_frac_of_burst_peak": (value * gf / 1e3 / world) / peaks["tf_burst"] if gf else None,
             "breakdown": breakdown,
+            "strong": strong,
+            "gpu_eager_baseline": eager,
+            "other_configs": other or None,
             "cpu_baseline": cpu_base,
-            "workspace_gb": model.workspace_bytes() / 2 ** 30,
+            "workspace_gb": workspace_gb,
         }
+        if eager:
+            for k in ("fp32_no_tf32", "bf16_autocast"):
+                if eager.get(k, {}).get("images_per_s"):
+                    eager[k]["speedup_of_this_repo"] = value / eager[k]["images_per_s"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

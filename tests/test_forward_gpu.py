@@ -17,6 +17,34 @@ from tests.golden_util import golden_names, load_golden, sample
 pytestmark = pytest.mark.gpu
 
 REL_TOL, ABSREL_TOL = 1e-2, 1e-3
+# Intermediates, max |got - ref| / max |ref| over the strided golden sample. Bars = 2x the largest value measured on a B200
+# over the eight goldens (gpurun_out/parity_report.json of round 2); bf16 activations, fp32 accumulation / residual stream.
+INTER_TOL = {"tokens": 4e-3, "tap": 2e-2, "layer": 2e-2, "layer_rn": 2e-2, "path": 2e-2}
+
+
+def _inter_kind(k):
+    if k == "tokens":
+        return "tokens"
+    if k.startswith("tap"):
+        return "tap"
+    if k.startswith("layer"):
+        return "layer_rn" if k.endswith("_rn") else "layer"
+    return "path"
+
+
+def _record(name, report):
+    """Keeps the measured errors of a GPU run (gpurun_out/ travels back from the GPU box) so the bars above can be audited."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "parity_report.json")
+        allr = json.load(open(path)) if os.path.exists(path) else {}
+        allr[name] = report
+        json.dump(allr, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
 
 
 def _model(enc, gt, ls, sd):
@@ -54,20 +82,20 @@ def test_forward_matches_reference_golden(name):
         if not key.startswith("s_"):
             continue
         k = key[2:]
-        if k in ("logits",) or k.startswith("layer") and not k.endswith("_rn"):
-            continue
-        numel = {"tokens": None}.get(k)
-        try:
-            n = _numel(meta, k)
-            got = m.read_intermediate(k, n)
-        except Exception as e:  # noqa: BLE001
-            report[k] = f"unavailable: {e}"
-            continue
-        got = _to_ref_layout(meta, k, got)
-        g = sample(got)
+        if k == "logits":
+            continue  # checked below from the output (the fused tail never stores the pre-sigmoid map)
+        got = m.read_intermediate(k, _numel(meta, k))   # an unreadable intermediate is a failure, not a skip
+        g = sample(_to_ref_layout(meta, k, got))
         scale = float(np.abs(z[key]).max())
         report[k] = float(np.abs(g - z[key]).max() / scale)
-        assert report[k] < 5e-2, (k, report)
+        assert report[k] < INTER_TOL[_inter_kind(k)], (k, report)
+    if "s_logits" in z.files and "ssi" not in meta["loss_stategy"]:
+        # pre-sigmoid logits (dpt.py:195, output_conv2[2]) recovered from the fp32 output: logit = log(o / (1 - o))
+        lg = sample(torch.log(out.double() / (1.0 - out.double())).float())
+        report["logits_abs"] = float(np.abs(lg - z["s_logits"]).max())
+        report["logits_span"] = float(np.abs(z["s_logits"]).max())
+        assert report["logits_abs"] < (0.15 if meta["stress"] else 2e-2), report
+    _record(name, report)
     if "ssi" in meta["loss_stategy"]:   # raw logits (dpt.py:138-144): absolute bar, the output crosses zero
         err = (out - ref).abs().max().item()
         print(name, "logit max abs err", err, report)
@@ -75,6 +103,7 @@ def test_forward_matches_reference_golden(name):
         return
     rel, absrel = _errors(out, ref, inp["mask01"])
     print(name, f"rel {rel:.3e} absrel {absrel:.3e}", report)
+    _record(name, dict(report, rel=rel, absrel=absrel))
     if meta["stress"]:
         # stated looser bar for the stress init: bf16 operands cannot hold 1e-2 per pixel when logits span +-3
         # (torch's own autocast-bf16 reaches 3.5e-2 there)
@@ -97,6 +126,9 @@ def _numel(meta, k):
     if k.endswith("_rn"):
         i = int(k[5]) - 1
         return B * sh[i] * sw[i] * F
+    if k.startswith("layer"):   # input_projection output (dpt.py:178-179): C_i channels at level i
+        i = int(k[5]) - 1
+        return B * sh[i] * sw[i] * c["out_channels"][i]
     if k.startswith("path_"):
         i = int(k[5])
         ph = [0, sh[0] * 2, sh[0], sh[1], sh[2]]
@@ -111,6 +143,8 @@ def _to_ref_layout(meta, k, t):
     if k == "tokens" or k.startswith("tap"):
         return t
     B, F = meta["B"], c["features"]
+    if k.startswith("layer") and not k.endswith("_rn"):
+        F = c["out_channels"][int(k[5]) - 1]
     hw = t.numel() // (B * F)
     gh, gw = meta["H"] // 14, meta["W"] // 14
     # recover (h, w) from the pyramid level

@@ -41,9 +41,9 @@ def test_unguided_forward_matches_reference_golden(name):
         assert err <= 1e-3
 
 
-def test_unguided_vitg_518_matches_oracle_pipeline_shape():
-    """infer.py:16-21 usage: ViT-G un-guided model at 518x518 (ViT-S here keeps the CPU oracle fast; ViT-G is covered by
-    the golden above), output squeezed to [B,H,W], then min-max normalised by the caller."""
+def test_unguided_vits_518_matches_oracle_pipeline_shape():
+    """infer.py:16-21 usage at 518x518 on the small encoder: output squeezed to [B,H,W], then min-max normalised by the
+    caller. (The ViT-G model infer.py:59-61 really builds is the next test.)"""
     meta = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384])
     sd = synth.make_state_dict_raw("vits", 64, meta["out_channels"], 21)
     x = O.normalize_rgb(synth.make_inputs(1, 518, 518, 21)["x"])
@@ -52,3 +52,18 @@ def test_unguided_vitg_518_matches_oracle_pipeline_shape():
     rel = ((out - ref).abs() / ref.clamp_min(1e-6)).max().item()
     print("raw vits 518 rel", rel)
     assert out.shape == (1, 518, 518) and rel <= 1e-2
+
+
+def test_unguided_vitg_518_matches_oracle():
+    """The observation model exactly as infer.py:59-61 builds it -- DepthAnythingV2(encoder='vitg', features=384,
+    out_channels=[1536]*4) -- at 518x518, one image, against the CPU oracle (~10 s on the GPU box's host cores)."""
+    meta = dict(encoder="vitg", features=384, out_channels=[1536] * 4)
+    sd = synth.make_state_dict_raw("vitg", 384, meta["out_channels"], 27)
+    x = O.normalize_rgb(synth.make_inputs(1, 518, 518, 27)["x"])
+    ref = O.forward_raw(sd, "vitg", x)
+    out = _model(meta, sd)(x.cuda()).cpu()
+    pos = ref > 1e-3
+    rel = ((out - ref).abs()[pos] / ref[pos]).max().item()
+    err = (out - ref).abs().max().item()
+    print("raw vitg 518 rel", rel, "abs", err, "positive share", pos.float().mean().item())
+    assert out.shape == (1, 518, 518) and rel <= 1e-2 and err <= 1e-2 * ref.max().item()
