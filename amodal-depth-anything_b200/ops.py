@@ -19,10 +19,11 @@ def _stream(t=None):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _on(t):
-    """Context that makes `t`'s device current for the duration of a C-ABI call: the library launches on the current
-    device, so an operand on cuda:1 while cuda:0 is current must switch first."""
-    return torch.cuda.device(t.device)
+def _call(t, fn, *args):
+    """Runs one C-ABI entry point with `t`'s device current (the library launches on the current device, so an operand on
+    cuda:1 while cuda:0 is current must switch first) on that device's current stream."""
+    with torch.cuda.device(t.device):
+        L.check(fn(*args, _stream(t)))
 
 
 def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,

@@ -17,9 +17,12 @@ from tests.golden_util import golden_names, load_golden, sample
 pytestmark = pytest.mark.gpu
 
 REL_TOL, ABSREL_TOL = 1e-2, 1e-3
-# Intermediates, max |got - ref| / max |ref| over the strided golden sample. Bars = 2x the largest value measured on a B200
-# over the eight goldens (gpurun_out/parity_report.json of round 2); bf16 activations, fp32 accumulation / residual stream.
+# Intermediates, max |got - ref| / max |ref| over the strided golden sample; bf16 activations, fp32 accumulation / residual
+# stream. Largest values measured on a B200 over the eight goldens (round 2, gpurun_out/parity_report.json): tokens 2.6e-3,
+# taps 1.55e-2 (ViT-G, 40 blocks), layerN 1.48e-2, layerN_rn 1.15e-2, path_k 1.23e-2 -- the bars sit 1.3-1.7x above them.
 INTER_TOL = {"tokens": 4e-3, "tap": 2e-2, "layer": 2e-2, "layer_rn": 2e-2, "path": 2e-2}
+# pre-sigmoid logits, absolute: measured <= 1.4e-3 (default init, |logit| <= 0.11) and 2.6e-2 (stress init, |logit| <= 2.7)
+LOGIT_TOL, LOGIT_TOL_STRESS = 3e-3, 6e-2
 
 
 def _inter_kind(k):
@@ -94,7 +97,7 @@ def test_forward_matches_reference_golden(name):
         lg = sample(torch.log(out.double() / (1.0 - out.double())).float())
         report["logits_abs"] = float(np.abs(lg - z["s_logits"]).max())
         report["logits_span"] = float(np.abs(z["s_logits"]).max())
-        assert report["logits_abs"] < (0.15 if meta["stress"] else 2e-2), report
+        assert report["logits_abs"] < (LOGIT_TOL_STRESS if meta["stress"] else LOGIT_TOL), report
     _record(name, report)
     if "ssi" in meta["loss_stategy"]:   # raw logits (dpt.py:138-144): absolute bar, the output crosses zero
         err = (out - ref).abs().max().item()
