@@ -20,6 +20,7 @@
 
 #include "../../include/amodal_b200.h"
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "elementwise.cuh"
 #include "postproc.cuh"
 #include "evalops.cuh"
@@ -414,7 +415,16 @@ static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bf
   ++g_launches;
 }
 
-static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st) {
+template <int EMU, bool STAGGER, int WAITP>
+static void launch_attention_fa(const CUtensorMap& tm, const CUtensorMap& tmo, const FaArgs& fa, cudaStream_t st) {
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(attention_fa_kernel<EMU, STAGGER, WAITP>, kFaSmemBytes, attr_done);
+  const int grid = std::min(fa.total_units, device_info().sms);  // persistent: one CTA per SM
+  launch_pdl(attention_fa_kernel<EMU, STAGGER, WAITP>, dim3(grid), dim3(kFaThreads), kFaSmemBytes, st, tm, tmo, fa);
+}
+
+static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st,
+                             int force_impl = -1) {
   const int D = heads * 64;
   uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t str[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(N) * 3 * D * 2};
@@ -432,6 +442,54 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
+  // Two kernels. attention2.cuh (persistent CTAs, two query tiles per CTA, one thread per score row, three issuing warps)
+  // wins once every SM gets several 256-query work units: 10.1 vs 10.7 ms per step at batch 32 (20.8 units per SM),
+  // 16.3 vs 17.4 ms at 1036^2 batch 4 (9.5 units per SM). For small grids the 128-query CTAs of attention.cuh quantise
+  // better (batch 8: 0.103 vs 0.110 ms; batch 4: 0.056 vs 0.062 ms). ADA_ATT_IMPL = 0 / 1 forces one of them.
+  static const int impl_env = env_int("ADA_ATT_IMPL", -1);
+  FaArgs fa;
+  fa.B = B;
+  fa.N = N;
+  fa.heads = heads;
+  fa.D = D;
+  fa.units_per_seq = ((N + 127) / 128 + 1) / 2;
+  fa.total_units = B * heads * fa.units_per_seq;
+  fa.scale_log2e = a.scale_log2e;
+  const int impl_sel = force_impl >= 0 ? force_impl : impl_env;
+  const bool use_fa = impl_sel >= 0 ? impl_sel == 1 : fa.total_units >= 6 * device_info().sms;
+  if (use_fa) {
+#ifdef ADA_BRINGUP
+    // measurement variants (exponential split MUFU / FMA pipe, group stagger, placement of the P V wait); the sweeps are
+    // in profiles/README.md. The product library carries <0, false, 2> only.
+    static const int emu = env_int("ADA_ATT_EMU", 0);
+    static const int stagger = env_int("ADA_ATT_STAGGER", 0);
+    static const int waitp = env_int("ADA_ATT_WAIT", 2);
+#define ADA_FA_CASE(E)                                                                                  \
+  case E:                                                                                               \
+    if (stagger) {                                                                                      \
+      if (waitp == 0) launch_attention_fa<E, true, 0>(tm, tmo, fa, st);                                 \
+      else if (waitp == 1) launch_attention_fa<E, true, 1>(tm, tmo, fa, st);                            \
+      else launch_attention_fa<E, true, 2>(tm, tmo, fa, st);                                            \
+    } else {                                                                                            \
+      if (waitp == 0) launch_attention_fa<E, false, 0>(tm, tmo, fa, st);                                \
+      else if (waitp == 1) launch_attention_fa<E, false, 1>(tm, tmo, fa, st);                           \
+      else launch_attention_fa<E, false, 2>(tm, tmo, fa, st);                                           \
+    }                                                                                                   \
+    break;
+    switch (emu) {
+      ADA_FA_CASE(0)
+      ADA_FA_CASE(4)
+      ADA_FA_CASE(6)
+      default: throw AdaError(ADA_EINVAL, "ADA_ATT_EMU must be one of 0, 4, 6");
+    }
+#undef ADA_FA_CASE
+#else
+    launch_attention_fa<0, false, 2>(tm, tmo, fa, st);
+#endif
+    ADA_CHECK_CUDA(cudaGetLastError());
+    ++g_launches;
+    return;
+  }
 #ifdef ADA_BRINGUP
   // measurement variants of the kernel (attention.cuh: exponential placement, timing skeleton, clock64 timeline) exist only
   // in bring-up builds (-DADA_BRINGUP); the product library carries variant 0 alone.
@@ -1828,11 +1886,12 @@ int ada_eval_sample(const float* pred, int32_t h, int32_t w, const float* depth_
   });
 }
 
-int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream) {
+int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, int32_t impl, void* stream) {
   return guarded([&] {
     require_device();
+    ADA_REQUIRE(qkv_bf16 && out_bf16 && B > 0 && N > 0 && heads > 0 && impl >= -1 && impl <= 1, "bad argument");
     launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, N, heads,
-                     static_cast<cudaStream_t>(stream));
+                     static_cast<cudaStream_t>(stream), impl);
   });
 }
 

@@ -167,8 +167,9 @@ int ada_post_blend_seam(const float* raw01, const float* amodal, const float* ma
 int ada_eval_sample(const float* pred, int32_t h, int32_t w, const float* depth_gt, const float* depth_obs,
                     const uint8_t* visible_mask, const uint8_t* object_mask, int32_t H, int32_t W, double* out24,
                     double* scratch26, void* stream);
-/* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). */
-int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, void* stream);
+/* qkv bf16 [B,N,3,heads,64] -> out bf16 [B,N,heads*64] (attention.py:49-62). impl: -1 = the kernel ada_forward would pick for
+ * this shape, 0 = attention.cuh (one 128-query tile per CTA), 1 = attention2.cuh (persistent, 256 queries per work unit). */
+int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, int32_t impl, void* stream);
 /* NHWC bf16 channel LayerNorm + ReLU (dpt.py:56-61,156-158). */
 int ada_op_channel_ln_relu(const void* in_bf16, const float* w, const float* b, void* out_bf16, int64_t pixels, int32_t C,
                            float eps, void* stream);

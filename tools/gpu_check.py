@@ -140,7 +140,7 @@ def chk_convT(ks):
     return _cmp("convT", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
 
 
-def chk_attention(B, N, heads, grow=False):
+def chk_attention(B, N, heads, grow=False, impl=-1):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(5)
     D = heads * 64
@@ -149,7 +149,7 @@ def chk_attention(B, N, heads, grow=False):
         ramp = 1.0 + 7.0 * (torch.arange(N, device="cuda") // 128).float() / max((N - 1) // 128, 1)
         qkv[:, :, 1] *= ramp.view(1, N, 1, 1)
     qkv = qkv.bfloat16()
-    out = ops.attention(qkv, B, N, heads)
+    out = ops.attention(qkv, B, N, heads, impl)
     torch.cuda.synchronize()
     q, k, v = [t.float().permute(0, 2, 1, 3) for t in qkv.unbind(2)]  # [B,h,N,64]
     att = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1)
@@ -330,11 +330,18 @@ CHECKS = {
     "conv_tail": lambda: chk_conv(1, 70, 84, 64, 32, "tail"),
     "convT_k4": lambda: chk_convT(4),
     "convT_k2": lambda: chk_convT(2),
-    "attention_small": lambda: chk_attention(1, 128, 1),
-    "attention_ragged": lambda: chk_attention(1, 200, 2),
-    "attention_1370": lambda: chk_attention(2, 1370, 6),
-    "attention_rescale": lambda: chk_attention(1, 1370, 2, grow=True),
-    "attention_5477": lambda: chk_attention(1, 5477, 2),
+    # both attention kernels on every shape (impl 0 = attention.cuh, 1 = attention2.cuh), then the auto-selected one
+    **{f"attention{i}_small": (lambda i=i: chk_attention(1, 128, 1, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_ragged": (lambda i=i: chk_attention(1, 200, 2, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_1370": (lambda i=i: chk_attention(2, 1370, 6, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_rescale": (lambda i=i: chk_attention(1, 1370, 2, grow=True, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_5477": (lambda i=i: chk_attention(1, 5477, 2, impl=i)) for i in (0, 1)},
+    # persistent kernel: several work units per CTA, full (two query tiles) and short (one tile) units interleaved
+    **{f"attention{i}_multiunit_1370": (lambda i=i: chk_attention(4, 1370, 16, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_multiunit_300": (lambda i=i: chk_attention(8, 300, 16, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_multiunit_128": (lambda i=i: chk_attention(10, 128, 16, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_multiunit_rescale": (lambda i=i: chk_attention(3, 700, 16, grow=True, impl=i)) for i in (0, 1)},
+    "attention_auto_b32": lambda: chk_attention(32, 1370, 16),
     "layernorm_384": lambda: chk_layernorm(384, False),
     "layernorm_1024_drop": lambda: chk_layernorm(1024, True),
     "layernorm_1536": lambda: chk_layernorm(1536, False),
