@@ -30,7 +30,7 @@
 
 namespace ada {
 
-constexpr int kAttThreads = 320;
+constexpr int kAttThreads = 384;   // warps 0..3: producer, score issuer, P V issuer, idle; warps 4..11: softmax
 constexpr int kAttSoftmaxThreads = 256;
 constexpr int kAttQ = 128, kAttKV = 128, kAttD = 64;
 constexpr int kAttSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 3072 /*pair exchange*/ + 256 /*barriers*/;
@@ -103,6 +103,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
+  // registers: compiled for 80 per thread (two CTAs of 12 warps per SM); the control warpgroup keeps 48, the two softmax
+  // warpgroups take 96 (setmaxnreg)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, elected lane per instruction)
     mbar_expect_tx_w(q_full, 16384);
@@ -120,10 +124,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
     const uint64_t dq = make_smem_desc_sw128(sQ, 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(sK, 16, 1024);
-    const uint64_t dv0 = make_smem_desc_sw128(sV, 0, 1024);
     auto issue_s = [&](int j) {
       const int s = j & 1;
       mbar_wait(k_full(s), (j >> 1) & 1, 0x520 + s);
@@ -143,17 +145,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
 #endif
     mbar_wait(q_full, 0, 0x530);
     issue_s(0);
+    for (int j = 0; j + 1 < num_kv; ++j) {
+      named_bar_sync(6, kAttSoftmaxThreads + 32);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
+      issue_s(j + 1);
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ P V issuer, on another scheduler than the score
+    // issuer: a tcgen05.mma shares its scheduler's MIO queue with the MUFU instructions of the softmax warps living there
+    // (~100 cycles per MMA to get through it); with the 12 MMAs of a tile issued by one warp -- and the issuers of both
+    // resident CTAs on the same scheduler -- MMA issue was what bounded the kernel (clock64 timelines, profiles/README.md).
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+    const uint64_t dv0 = make_smem_desc_sw128(sV, 0, 1024);
     for (int j = 0; j < num_kv; ++j) {
       const int s = j & 1;
-      istamp(j, 0);
-      if (j + 1 < num_kv) {
-        named_bar_sync(6, kAttSoftmaxThreads + 32);  // softmax has pulled S(j) into registers -> S(j+1) may overwrite it
-        istamp(j, 1);
-        issue_s(j + 1);
-      }
-      istamp(j, 2);
       named_bar_sync(7, kAttSoftmaxThreads + 32);  // P(j) in TMEM, O rescaled if needed
-      istamp(j, 3);
       mbar_wait(v_full(s), (j >> 1) & 1, 0x550 + s);
       tc_fence_after();
 #pragma unroll
@@ -161,19 +166,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         umma_bf16_ts_w(tO, tP + kk * 8, dv0 + s * 1024 + kk * 128, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
       umma_commit_w(v_empty(s));
       umma_commit_w(o_full);
-      istamp(j, 4);
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     // ------------------------------------------------------------------ softmax / output warps
     const int qd = warp & 3;               // TMEM lane quarter
-    const int half = (warp - 2) >> 2;      // which 64 score columns of the row this thread owns
+    const int half = (warp - 4) >> 2;      // which 64 score columns of the row this thread owns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float c = a.scale_log2e;
     float m_used = -INFINITY, l_part = 0.f;
 
 #ifdef ADA_BRINGUP
-    const bool tl = (VARIANT == 10) && threadIdx.x == 64 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
+    const bool tl = (VARIANT == 10) && threadIdx.x == 128 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7;
     auto stamp = [&](int j, int k) {
       if (tl) g_dev_timeline[j * 8 + k] = clock64();
     };
@@ -336,7 +342,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     }
     fence_proxy_async_smem();
     named_bar_sync(5, kAttSoftmaxThreads);
-    if (threadIdx.x == 64) {  // first softmax thread; rows past N are clipped by the tensor map
+    if (threadIdx.x == 128) {  // first softmax thread; rows past N are clipped by the tensor map
       tma_store_3d(&tmap_out, sQ, head * kAttD, q0, img);
       bulk_commit();
       bulk_wait<0>();
