@@ -460,8 +460,8 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   if (use_fa) {
 #ifdef ADA_BRINGUP
     // measurement variants (exponential split MUFU / FMA pipe, group stagger, placement of the P V wait); the sweeps are
-    // in profiles/README.md. The product library carries <0, false, 2> only.
-    static const int emu = env_int("ADA_ATT_EMU", 0);
+    // in profiles/README.md. The product library carries <6, false, 2> only.
+    static const int emu = env_int("ADA_ATT_EMU", 6);
     static const int stagger = env_int("ADA_ATT_STAGGER", 0);
     static const int waitp = env_int("ADA_ATT_WAIT", 2);
 #define ADA_FA_CASE(E)                                                                                  \
@@ -484,7 +484,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
     }
 #undef ADA_FA_CASE
 #else
-    launch_attention_fa<0, false, 2>(tm, tmo, fa, st);
+    launch_attention_fa<6, false, 2>(tm, tmo, fa, st);
 #endif
     ADA_CHECK_CUDA(cudaGetLastError());
     ++g_launches;

@@ -60,6 +60,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 
 // bit p set = exponential pair p (of every 16) runs on the FMA pipe; EMU of 16, evenly spaced
 __host__ __device__ constexpr uint32_t fa_emu_mask(int emu) {
+  if (emu == 6) return 0x9249u;  // the pattern attention.cuh uses: both kernels then produce bit-identical results
   uint32_t m = 0;
   for (int p = 0; p < 16; ++p)
     if ((p * emu) % 16 < emu) m |= 1u << p;
@@ -308,7 +309,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     for (int idx = blockIdx.x; idx < a.total_units; idx += gridDim.x) {
       const FaUnit u = fa_unit(idx, a);
       if (!u.valid[t]) continue;
-      float m_used = -INFINITY, l_sum = 0.f;
+      float m_used = -INFINITY, l_sum[2] = {0.f, 0.f};
       if (STAGGER && t == 1) named_bar_sync(kBarStagger, 256);
 
       // One KV tile. MASKED (compile-time): only the ragged last tile carries the 128 compare+select pairs that overwrite
@@ -374,7 +375,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             const float m_new = fmaxf(m_used, tmax);
             sc = fast_exp2((m_used - m_new) * c);
             m_used = m_new;
-            l_sum *= sc;
+            l_sum[0] *= sc;
+            l_sum[1] *= sc;
           }
           if (rescale || WAITP == 0) {
             // P_t(j-1) V_{j-1} must have retired before O_t may be rescaled (WAITP == 0: and before P_t is overwritten)
@@ -399,7 +401,10 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         // it exists (16 packed columns) and the score registers die progressively
         constexpr uint32_t kEmuMask = fa_emu_mask(EMU);
         const uint64_t c2 = f2_pack(c, c), nmc2 = f2_pack(-mc, -mc);
-        uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};  // independent packed row-sum chains
+        // independent packed row-sum chains, kept apart for columns 0..63 and 64..127: the same summation order as the two
+        // threads that share a row in attention.cuh, so that the two kernels agree bit for bit (an image must not change
+        // with the batch size it is processed in, and the kernel is selected by grid size)
+        uint64_t rs2[2][4] = {{0ull, 0ull, 0ull, 0ull}, {0ull, 0ull, 0ull, 0ull}};
         uint32_t pk[4][16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -419,7 +424,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
-            rs2[(i >> 1) & 3] = f2_add(rs2[(i >> 1) & 3], f2_pack(p0, p1));
+            rs2[q >> 1][(i >> 1) & 3] = f2_add(rs2[q >> 1][(i >> 1) & 3], f2_pack(p0, p1));
             pk[q][i >> 1] = pack_bf16x2(p0, p1);
           }
           }
@@ -441,10 +446,11 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           for (int q = 0; q < 4; ++q) tmem_st16(tP + 16 * q, pk[q]);
         }
         if (j > 0) ofp ^= 1u;
-        {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           float a0, a1;
-          f2_unpack(f2_add(f2_add(rs2[0], rs2[1]), f2_add(rs2[2], rs2[3])), a0, a1);
-          l_sum += a0 + a1;
+          f2_unpack(f2_add(f2_add(rs2[h][0], rs2[h][1]), f2_add(rs2[h][2], rs2[h][3])), a0, a1);
+          l_sum[h] += a0 + a1;
         }
         stamp(j, 5);
         tmem_st_wait();
@@ -471,7 +477,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free(t));  // O_t may be overwritten by the next unit's first P V
-      const float inv = 1.0f / l_sum;
+      const float inv = 1.0f / (l_sum[0] + l_sum[1]);
       if (gthread == 0 && stored) bulk_wait_read<0>();  // the previous unit's store has finished reading the staging tile
       named_bar_sync(kBarWG + t, 128);
       const uint32_t o_row = sO + static_cast<uint32_t>(row) * 128u;

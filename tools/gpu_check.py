@@ -157,6 +157,23 @@ def chk_attention(B, N, heads, grow=False, impl=-1):
     return _cmp("attention", out, ref, 2e-2, 2e-2)
 
 
+def chk_attention_impls_agree(B, N, heads, grow=False):
+    """The two attention kernels are selected by grid size; an image must not change with the batch it is processed in, so
+    they have to agree bit for bit (same exponential evaluation per column, same summation order of the row sums)."""
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(15)
+    qkv = torch.randn(B, N, 3, heads, 64, generator=g, device="cuda") * 1.5
+    if grow:
+        ramp = 1.0 + 7.0 * (torch.arange(N, device="cuda") // 128).float() / max((N - 1) // 128, 1)
+        qkv[:, :, 1] *= ramp.view(1, N, 1, 1)
+    qkv = qkv.bfloat16()
+    a = ops.attention(qkv, B, N, heads, 0)
+    b = ops.attention(qkv, B, N, heads, 1)
+    torch.cuda.synchronize()
+    diff = (a.float() - b.float()).abs()
+    return {"ok": bool(torch.equal(a, b)), "max_abs": diff.max().item(), "n_diff": int((diff > 0).sum().item()), "n": a.numel()}
+
+
 def chk_layernorm(D, drop):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(6)
@@ -342,6 +359,9 @@ CHECKS = {
     **{f"attention{i}_multiunit_128": (lambda i=i: chk_attention(10, 128, 16, impl=i)) for i in (0, 1)},
     **{f"attention{i}_multiunit_rescale": (lambda i=i: chk_attention(3, 700, 16, grow=True, impl=i)) for i in (0, 1)},
     "attention_auto_b32": lambda: chk_attention(32, 1370, 16),
+    "attention_impls_agree_1370": lambda: chk_attention_impls_agree(3, 1370, 16),
+    "attention_impls_agree_rescale": lambda: chk_attention_impls_agree(2, 700, 16, grow=True),
+    "attention_impls_agree_5477": lambda: chk_attention_impls_agree(1, 5477, 4),
     "layernorm_384": lambda: chk_layernorm(384, False),
     "layernorm_1024_drop": lambda: chk_layernorm(1024, True),
     "layernorm_1536": lambda: chk_layernorm(1536, False),
