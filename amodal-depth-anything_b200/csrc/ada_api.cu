@@ -302,7 +302,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
 #else
   g.debug_timeline = 0;
 #endif
-  if (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU) {
+  if (g.epi == EPI_BF16 || g.epi == EPI_F16 || g.epi == EPI_SWIGLU) {
     const int n_out = (g.epi == EPI_SWIGLU) ? L.N / 2 : L.N;
     ADA_REQUIRE(g.out_bf16 != nullptr && g.ldo % 8 == 0 && n_out % 8 == 0, "bf16 output needs ldo, N multiples of 8");
     auto make_c = [&](const void* ptr) {
@@ -344,6 +344,13 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   if (g.epi == EPI_BF16) {
     const bool resid = g.resid1 != nullptr || g.resid2 != nullptr;
     ADA_REQUIRE(!(resid && g.act == ACT_GELU), "EPI_BF16: GELU and residual adds are not combined on this path");
+  }
+  if (g.epi == EPI_F16) {
+    ADA_REQUIRE(g.act == ACT_NONE && g.resid1 == nullptr && g.resid2 == nullptr && L.out_relu == nullptr,
+                "EPI_F16: no activation, residuals or ReLU copy");
+  }
+  if (g.epi == EPI_BF16) {
+    const bool resid = g.resid1 != nullptr || g.resid2 != nullptr;
     epi_t = resid ? EPI_BF16_RESID : (g.act == ACT_GELU) ? EPI_BF16_GELU : (g.act == ACT_RELU) ? EPI_BF16_RELU : EPI_BF16;
   }
 #define ADA_GEMM_CASE(BN_, CG_, EPI_)                                      \
@@ -372,6 +379,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_GEMM_CASE(128, 2, EPI_BF16_RESID)
   ADA_GEMM_CASE(256, 1, EPI_BF16_RESID)
   ADA_GEMM_CASE(256, 2, EPI_BF16_RESID)
+  ADA_GEMM_CASE(64, 1, EPI_F16)
+  ADA_GEMM_CASE(128, 1, EPI_F16)
+  ADA_GEMM_CASE(256, 1, EPI_F16)
+  ADA_GEMM_CASE(256, 2, EPI_F16)
   ADA_GEMM_CASE(64, 1, EPI_RESID_F32)
   ADA_GEMM_CASE(128, 1, EPI_RESID_F32)
   ADA_GEMM_CASE(256, 1, EPI_RESID_F32)
@@ -442,10 +453,13 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   a.scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid((N + kAttQ - 1) / kAttQ, heads, B);
   ProfScope prof(PC_ATTENTION, 4.0 * B * heads * static_cast<double>(N) * N * 64.0, 8.0 * B * static_cast<double>(N) * D, st);
-  // Two kernels. attention2.cuh (persistent CTAs, two query tiles per CTA, one thread per score row, three issuing warps)
-  // wins once every SM gets several 256-query work units: 10.1 vs 10.7 ms per step at batch 32 (20.8 units per SM),
-  // 16.3 vs 17.4 ms at 1036^2 batch 4 (9.5 units per SM). For small grids the 128-query CTAs of attention.cuh quantise
-  // better (batch 8: 0.103 vs 0.110 ms; batch 4: 0.056 vs 0.062 ms). ADA_ATT_IMPL = 0 / 1 forces one of them.
+  // Two kernels that agree bit for bit (tools/gpu_check.py attention_impls_agree_*). attention.cuh (one 128-query tile per
+  // CTA, two CTAs per SM, a score row shared by two threads) is the product path. attention2.cuh (persistent CTAs, 256
+  // queries per work unit, one thread per score row, three issuing warps) is selectable with ADA_ATT_IMPL=1 / impl = 1 of
+  // ada_op_attention: round-2 measurements (profiles/README.md) put it 3-6 % ahead stand-alone and in the model when ALL
+  // its exponentials run on MUFU (10.1-10.4 vs 10.7-10.8 ms per step at batch 32, 16.3 vs 17.4 ms at 1036^2), but level or
+  // behind (11.25 vs 10.7 ms) with the 6/16 FMA-pipe split that bit-identity with attention.cuh requires -- and an image
+  // must not change with the batch size it is processed in, so the kernel choice may not depend on the grid.
   static const int impl_env = env_int("ADA_ATT_IMPL", -1);
   FaArgs fa;
   fa.B = B;
@@ -456,7 +470,7 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   fa.total_units = B * heads * fa.units_per_seq;
   fa.scale_log2e = a.scale_log2e;
   const int impl_sel = force_impl >= 0 ? force_impl : impl_env;
-  const bool use_fa = impl_sel >= 0 ? impl_sel == 1 : fa.total_units >= 6 * device_info().sms;
+  const bool use_fa = impl_sel == 1;
   if (use_fa) {
 #ifdef ADA_BRINGUP
     // measurement variants (exponential split MUFU / FMA pipe, group stagger, placement of the P V wait); the sweeps are
@@ -549,7 +563,7 @@ static void launch_upsample(const __nv_bfloat16* in, __nv_bfloat16* out, int B, 
   ++g_launches;
 }
 
-static void launch_tail_gather(const __nv_bfloat16* V, const float* bias2, const float* aux, float* out, int B, int Hl,
+static void launch_tail_gather(const __half* V, const float* bias2, const float* aux, float* out, int B, int Hl,
                                int Wl, int H, int W, int sigmoid, cudaStream_t st) {
   static std::atomic<uint64_t> attr_done{0};
   ensure_smem_attr(tail_gather_kernel, kTailSmemBytes, attr_done);
@@ -1435,7 +1449,7 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st);
   if (tail_fused(ph[1], pw[1], H, W)) {
     GemmArgs e{};
-    e.epi = EPI_BF16;
+    e.epi = EPI_F16;  // the tap map is stored as fp16 (tail_gather_kernel interpolates it with packed fp16 FMAs)
     e.out_bf16 = m->vtap;
     e.ldo = 288;
     {
@@ -1454,7 +1468,7 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
       L.force_bn = tail_bn;
       launch_gemm(L, st);
     }
-    launch_tail_gather(m->vtap, m->oc2.b, m->tail_aux, out, B, ph[1], pw[1], H, W, c.sigmoid, st);
+    launch_tail_gather(reinterpret_cast<const __half*>(m->vtap), m->oc2.b, m->tail_aux, out, B, ph[1], pw[1], H, W, c.sigmoid, st);
   } else {
     launch_upsample(m->oc1b, m->up, B, ph[1], pw[1], H, W, F / 2, st);
     GemmLaunch L;
@@ -1930,11 +1944,11 @@ int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, 
   });
 }
 
-int ada_op_tail_gather(const void* v_bf16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
+int ada_op_tail_gather(const void* v_f16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
                        int32_t H, int32_t W, int32_t sigmoid, void* stream) {
   return guarded([&] {
     require_device();
-    launch_tail_gather(static_cast<const __nv_bfloat16*>(v_bf16), bias2, aux, out, B, Hl, Wl, H, W, sigmoid,
+    launch_tail_gather(static_cast<const __half*>(v_f16), bias2, aux, out, B, Hl, Wl, H, W, sigmoid,
                        static_cast<cudaStream_t>(stream));
   });
 }

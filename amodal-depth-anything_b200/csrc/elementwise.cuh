@@ -299,7 +299,7 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
 // output_conv2 = conv3x3(F/2 -> 32) + ReLU + conv1x1(32 -> 1) + Sigmoid.
 // A 1x1 channel contraction commutes with bilinear resampling, and a 3x3 conv is a sum over taps of shifted 1x1
 // contractions, so the 32 x (F/2) contraction of EACH tap is applied at LOW resolution by a tcgen05 GEMM
-// (V[pix, tap*32 + co] = sum_ci W2[co, ci, tap] * y[pix, ci]; 3x fewer FLOPs than the conv at 14h x 14h) and this kernel
+// (V[pix, tap*32 + co] = sum_ci W2[co, ci, tap] * y[pix, ci], stored as fp16; 3x fewer FLOPs than the conv at 14h x 14h) and this kernel
 // finishes the job: out(p) = sigmoid(w3 . relu(b2 + sum_taps bilinear(V_tap)(p + d_tap)) + b3), taps that fall outside
 // the image contribute zero (the conv's zero padding). The 128-channel 14h x 14h map (2.2 GB at batch 32, re-read 9x
 // through L2 by the implicit-GEMM tail, which ran at 200 TFLOP/s) is never materialised.
@@ -312,7 +312,7 @@ constexpr int kTailPitch = kTailCh * 2 + 16;  // 592 B per low-res pixel: +16 B 
 constexpr int kTailSmemBytes = kTailPatch * kTailPatch * kTailPitch;
 
 __global__ void __launch_bounds__(256)
-tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict__ bias2, const float* __restrict__ aux,
+tail_gather_kernel(const __half* __restrict__ V, const float* __restrict__ bias2, const float* __restrict__ aux,
                    float* __restrict__ out, int Hl, int Wl, int H, int W, int apply_sigmoid) {
   extern __shared__ __align__(16) uint8_t tail_smem[];
   const int tid = threadIdx.x;
@@ -344,9 +344,12 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
   const int ty = tid >> 4, tx = tid & 15;
   const int Y = Y0 + ty, X = X0 + tx;
   if (Y >= H || X >= W) return;
-  uint64_t acc2[16];  // 32 fp32 accumulators as packed pairs (FFMA2: the kernel is issue bound, ~2300 instructions per pixel)
+  // The 9 x 4 x 32 interpolation FMAs per pixel are what bounds this kernel (issue slots, not HBM). The tap map is stored as
+  // fp16, so the four corners of the three taps of one kernel row are combined by packed fp16 FMAs (HFMA2: two channels
+  // per instruction, no unpacking; 12 terms of magnitude O(1) per fp16 sum), and the three row sums are added in fp32.
+  float acc[32];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc2[i] = f2_pack(__ldg(bias2 + 2 * i), __ldg(bias2 + 2 * i + 1));
+  for (int i = 0; i < 32; ++i) acc[i] = __ldg(bias2 + i);
   // per-tap source columns (three of them), rows handled in the loop
   int xo0[3], xo1[3];
   float lxv[3];
@@ -369,6 +372,9 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
     const int y0 = static_cast<int>(fy);
     const int yr0 = y0 - r0, yr1 = y0 + (y0 < Hl - 1 ? 1 : 0) - r0;
     const float ly = fy - y0, hy = 1.f - ly;
+    __half2 racc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) racc[i] = __float2half2_rn(0.f);
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       if (!xok[kx]) continue;
@@ -379,21 +385,24 @@ tail_gather_kernel(const __nv_bfloat16* __restrict__ V, const float* __restrict_
 #pragma unroll
       for (int cnr = 0; cnr < 4; ++cnr) {
         const uint4* p = reinterpret_cast<const uint4*>(tail_smem + pidx[cnr] * kTailPitch + tap * 64);
-        const uint64_t wv2 = f2_pack(wgt[cnr], wgt[cnr]);
+        const __half2 w2 = __float2half2_rn(wgt[cnr]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 v = p[q];
-          acc2[q * 4 + 0] = f2_fma(wv2, f2_pack(bf16_lo(v.x), bf16_hi(v.x)), acc2[q * 4 + 0]);
-          acc2[q * 4 + 1] = f2_fma(wv2, f2_pack(bf16_lo(v.y), bf16_hi(v.y)), acc2[q * 4 + 1]);
-          acc2[q * 4 + 2] = f2_fma(wv2, f2_pack(bf16_lo(v.z), bf16_hi(v.z)), acc2[q * 4 + 2]);
-          acc2[q * 4 + 3] = f2_fma(wv2, f2_pack(bf16_lo(v.w), bf16_hi(v.w)), acc2[q * 4 + 3]);
+          racc[q * 4 + 0] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.x), racc[q * 4 + 0]);
+          racc[q * 4 + 1] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.y), racc[q * 4 + 1]);
+          racc[q * 4 + 2] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.z), racc[q * 4 + 2]);
+          racc[q * 4 + 3] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.w), racc[q * 4 + 3]);
         }
       }
     }
-  }
-  float acc[32];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) f2_unpack(acc2[i], acc[2 * i], acc[2 * i + 1]);
+    for (int i = 0; i < 16; ++i) {
+      const float2 f = __half22float2(racc[i]);
+      acc[2 * i] += f.x;
+      acc[2 * i + 1] += f.y;
+    }
+  }
   float sres = __ldg(aux + 32);
 #pragma unroll
   for (int i = 0; i < 32; ++i) sres = fmaf(fmaxf(acc[i], 0.f), __ldg(aux + i), sres);

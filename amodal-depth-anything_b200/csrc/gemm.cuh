@@ -64,10 +64,14 @@ enum EpiMode : int {
   // warp's swizzled staging buffer by TMA (prefetched one 32-column block ahead), updated in shared memory and stored back
   // by TMA, so the fp32 residual stream of the encoder (block.py:105-106) is read and written coalesced, under the GEMM's
   // tensor time, instead of by the LayerNorm kernel (which drops from 14 / 8 to 6 bytes per element).
-  EPI_RESID_F32 = 9
+  EPI_RESID_F32 = 9,
+  // EPI_BF16 without activation / residuals, stored as IEEE fp16 instead of bf16: the per-tap contraction map of the fused
+  // tail (output_conv2.0 applied at low resolution), whose consumer interpolates it with packed fp16 FMAs. Values are O(1);
+  // fp16 keeps three more mantissa bits than bf16.
+  EPI_F16 = 10
 };
 __host__ __device__ constexpr bool epi_is_bf16(int e) {
-  return e == EPI_BF16 || e == EPI_BF16_GELU || e == EPI_BF16_RELU || e == EPI_BF16_RESID;
+  return e == EPI_BF16 || e == EPI_BF16_GELU || e == EPI_BF16_RELU || e == EPI_BF16_RESID || e == EPI_F16;
 }
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1 };
@@ -503,7 +507,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                   }
 #pragma unroll
-                  for (int j = 0; j < 8; j += 2) pk[h * 16 + gi * 4 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+                  for (int j = 0; j < 8; j += 2)
+                    pk[h * 16 + gi * 4 + (j >> 1)] = (EPI == EPI_F16) ? pack_f16x2(v[j], v[j + 1]) : pack_bf16x2(v[j], v[j + 1]);
                 }
               }
             }

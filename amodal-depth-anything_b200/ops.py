@@ -133,7 +133,7 @@ def pack_tail_taps(w):
 
 
 def tail_gather(V, bias2, aux, H, W, sigmoid=True):
-    """V: NHWC bf16 [B,Hl,Wl,288] -> fp32 [B,H,W]."""
+    """V: NHWC fp16 [B,Hl,Wl,288] -> fp32 [B,H,W]."""
     B, Hl, Wl, _ = V.shape
     out = torch.empty(B, H, W, dtype=torch.float32, device=V.device)
     _call(V, L.load().ada_op_tail_gather, _p(V), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, int(sigmoid))

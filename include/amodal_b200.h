@@ -117,7 +117,7 @@ typedef struct ada_gemm_desc {
   int32_t M, N, K, lda, ldb;
   int32_t a_mode;       /* 0 linear, 1 conv3x3 (pad 1, stride 1) */
   int32_t epi, act;     /* see EpiMode / ActMode in csrc/gemm.cuh (0 bf16 out, 2 embed, 3 convT, 4 tail, 5 SwiGLU,
-                           9 fp32 in-place residual: out_f32 += (acc + bias) * gamma) */
+                           9 fp32 in-place residual: out_f32 += (acc + bias) * gamma, 10 = mode 0 stored as IEEE fp16) */
   int32_t batch, H, W, Cin;   /* conv mode geometry; EPI_CONVT: input grid */
   const float* bias;
   const float* gamma;
@@ -182,9 +182,9 @@ int ada_op_patch_gather(const float* rgb, const float* const* guides, const int3
 /* stride-2 3x3 gather for resize_layers[3] (dpt.py:102-107): NHWC -> [B*Ho*Wo, 9*C]. */
 int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* Fused tail (dpt.py:194-195): V = per-tap 1x1 contractions of output_conv2.0 applied to the low-res output_conv1 map,
- * NHWC bf16 [B,Hl,Wl,288]; out[b,y,x] = sigmoid(w3 . relu(b2 + sum_taps bilinear_align_corners(V_tap)(y+dy, x+dx)) + b3),
+ * NHWC fp16 [B,Hl,Wl,288] (ada_op_gemm with epi = 10); out[b,y,x] = sigmoid(w3 . relu(b2 + sum_taps bilinear_align_corners(V_tap)(y+dy, x+dx)) + b3),
  * aux = [w3 (32), b3]. Requires the 8h -> 14h geometry (Hl*14 == H*8). */
-int ada_op_tail_gather(const void* v_bf16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
+int ada_op_tail_gather(const void* v_f16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
                        int32_t H, int32_t W, int32_t sigmoid, void* stream);
 /* output_conv2.0 weight [32,Cm,3,3] (host fp32) -> [(tap*32+co), Cm] bf16 on the device. */
 int ada_pack_tail_taps(const float* w_host, int32_t Cm, void* dst_dev_bf16);

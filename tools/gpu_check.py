@@ -261,8 +261,8 @@ def chk_fused_tail(gh, gw):
     ref = torch.sigmoid((z * w3.view(1, 32, 1, 1)).sum(1) + b3)
     wt = ops.pack_tail_taps(w2)
     ya = y.permute(0, 2, 3, 1).reshape(B * Hl * Wl, Cm).contiguous()
-    V = torch.zeros(B, Hl, Wl, 288, dtype=torch.bfloat16, device="cuda")
-    ops.gemm(ya, wt, out_bf16=V, ldo=288)
+    V = torch.zeros(B, Hl, Wl, 288, dtype=torch.float16, device="cuda")
+    ops.gemm(ya, wt, epi=L.EPI_F16, out_bf16=V, ldo=288)
     out = ops.tail_gather(V, b2, torch.cat([w3, b3]).contiguous(), H, W, True)
     torch.cuda.synchronize()
     return _cmp("fused_tail", out, ref, 5e-3, 0)
