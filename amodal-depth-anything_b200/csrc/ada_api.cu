@@ -536,12 +536,19 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
 static void launch_channel_ln_relu(const __nv_bfloat16* in, const float* w, const float* b, __nv_bfloat16* out,
                                    long long pixels, int C, float eps, cudaStream_t st) {
   ADA_REQUIRE(C % 8 == 0 && C <= 1536, "channel LN: C % 8 == 0 and C <= 1536");
-  const int grid = static_cast<int>(std::min<long long>((pixels + 15) / 16, 148LL * 8));  // persistent warps, 2 pixels in flight
+  const int sms = device_info().sms;
   ProfScope prof(PC_CHANNEL_LN, 0.0, 4.0 * pixels * static_cast<double>(C), st);
-  if (C <= 512)
-    channel_ln_relu_kernel<2, true><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+  auto grid_for = [&](int pix_per_warp, int blocks_per_sm) {  // persistent warps walking pixels with a grid stride
+    return static_cast<int>(std::min<long long>((pixels + 8 * pix_per_warp - 1) / (8 * pix_per_warp), static_cast<long long>(sms) * blocks_per_sm));
+  };
+  if (C <= 256)
+    channel_ln_relu_kernel<1, true, 4><<<grid_for(4, 8), 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+  else if (C <= 512)
+    channel_ln_relu_kernel<2, true, 2><<<grid_for(2, 8), 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+  else if (C <= 1024)
+    channel_ln_relu_kernel<4, false, 1><<<grid_for(1, 8), 256, 0, st>>>(in, w, b, out, pixels, C, eps);
   else
-    channel_ln_relu_kernel<6, false><<<grid, 256, 0, st>>>(in, w, b, out, pixels, C, eps);
+    channel_ln_relu_kernel<6, false, 1><<<grid_for(1, 8), 256, 0, st>>>(in, w, b, out, pixels, C, eps);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }

@@ -89,9 +89,11 @@ layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ d
 // ---------------------------------------------------------------------------------------------------------------
 // Channel LayerNorm + ReLU over NHWC bf16 pixels (channels_first LayerNorm of dpt.py:56-61 followed by nn.ReLU,
 // dpt.py:156-158). One warp per pixel, C % 8 == 0, C <= 8 * 32 * MAXG. In-place safe. Persistent: every warp walks
-// pixels with a grid stride, two pixels in flight per iteration, and (CACHE) keeps its lanes' weight / bias in registers
-// -- the one-pixel-per-warp version re-read 16 affine scalars per 8 channels and ran at 1.45 TB/s.
-template <int MAXG, bool CACHE>
+// pixels with a grid stride, PIXELS pixels in flight per iteration, and (CACHE) keeps its lanes' weight / bias in registers
+// -- the one-pixel-per-warp version re-read 16 affine scalars per 8 channels and ran at 1.45 TB/s. The kernel is latency
+// bound unless enough bytes are in flight per SM (Little: ~35 KB): <1, 4> for C <= 256 (one 16-byte group per lane, four
+// pixels = 2 KB per warp), <2, 2> up to 512 channels, <4, 1> / <6, 1> for 1024 / 1536.
+template <int MAXG, bool CACHE, int PIXELS>
 __global__ void __launch_bounds__(256)
 channel_ln_relu_kernel(const __nv_bfloat16* in, const float* __restrict__ w, const float* __restrict__ b,
                        __nv_bfloat16* out, long long pixels, int C, float eps) {
@@ -111,7 +113,7 @@ channel_ln_relu_kernel(const __nv_bfloat16* in, const float* __restrict__ w, con
       }
     }
   }
-  constexpr int PIX = CACHE ? 2 : 1;  // pixels in flight per warp
+  constexpr int PIX = PIXELS;  // pixels in flight per warp
   for (long long p0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * PIX; p0 < pixels; p0 += warps * PIX) {
     float v[PIX][MAXG][8];
     uint4 raw[PIX][MAXG];
@@ -240,14 +242,27 @@ im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Bilinear upsampling, align_corners=True (blocks.py:144, dpt.py:194), NHWC bf16. One thread per 8 channels.
-// Index math mirrors ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1).
-// Each thread produces kUpRows vertically adjacent output pixels (8 loads in flight before the first use).
-constexpr int kUpRows = 2;
+// Bilinear upsampling, align_corners=True (blocks.py:144, dpt.py:194), NHWC bf16. One thread = 8 channels of one output
+// column, walking a strip of kUpRows output rows. Index math mirrors ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst,
+// i0 = (int)src, i1 = i0 + (i0 < in-1). The first version (one thread per pair of output pixels, four corner loads and six
+// multiply-adds per value) was instruction bound at 3.1 TB/s (5.6 instructions per byte written). Here the horizontal
+// interpolation of a source row is computed once and kept in registers while the strip walks down: with the 2x maps of the
+// head every source row serves two output rows, so a value costs ~3 FMAs and half an unpack instead of 6 + 4.
+constexpr int kUpRows = 16;
+__device__ __forceinline__ void up_hlerp(const __nv_bfloat16* row, int x0c, int x1c, float hx, float lx, float (&o)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + x0c));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + x1c));
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[2 * j] = hx * bf16_lo(av[j]) + lx * bf16_lo(bv[j]);
+    o[2 * j + 1] = hx * bf16_hi(av[j]) + lx * bf16_hi(bv[j]);
+  }
+}
 __global__ void __launch_bounds__(256)
 upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Hi, int Wi, int Ho,
                          int Wo, int C, int groups_shift) {
-  // grid: x over (xo, 8-channel group), y = pair of output rows, z = image: no 64-bit div/mod on the hot path
+  // grid: x over (xo, 8-channel group), y = strip of output rows, z = image: no 64-bit div/mod on the hot path
   const int groups = C >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int xo = (groups_shift >= 0) ? (i >> groups_shift) : (i / groups);
@@ -261,36 +276,41 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __
   const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
   const float lx = fx - x0, hx = 1.f - lx;
   const __nv_bfloat16* base = in + static_cast<long long>(b) * Hi * Wi * C + gi * 8;
-  uint4 q[kUpRows][4];
-  float ly[kUpRows];
-#pragma unroll
-  for (int u = 0; u < kUpRows; ++u) {
-    const int yo = min(static_cast<int>(blockIdx.y) * kUpRows + u, Ho - 1);
+  const int x0c = x0 * C, x1c = x1 * C;
+  const long long rowpitch = static_cast<long long>(Wi) * C;
+  const int ybeg = static_cast<int>(blockIdx.y) * kUpRows, yend = min(ybeg + kUpRows, Ho);
+  float top[8], bot[8];
+  int cy0 = -1, cy1 = -1;  // source rows currently held in top / bot
+  __nv_bfloat16* dst = out + ((static_cast<long long>(b) * Ho + ybeg) * Wo + xo) * C + gi * 8;
+  for (int yo = ybeg; yo < yend; ++yo) {   // (all branches below are uniform over the block: they depend on yo only)
     const float fy = sh * yo;
     const int y0 = static_cast<int>(fy);
     const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
-    ly[u] = fy - y0;
-    q[u][0] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * C));
-    q[u][1] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * C));
-    q[u][2] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * C));
-    q[u][3] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * C));
-  }
+    const float ly = fy - y0, hy = 1.f - ly;
+    if (y0 != cy0) {
+      if (y0 == cy1) {
 #pragma unroll
-  for (int u = 0; u < kUpRows; ++u) {
-    const int yo = static_cast<int>(blockIdx.y) * kUpRows + u;
-    if (yo >= Ho) break;
-    const float hy = 1.f - ly[u];
-    const uint32_t av[4] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w}, bv[4] = {q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w},
-                   cv[4] = {q[u][2].x, q[u][2].y, q[u][2].z, q[u][2].w}, dv[4] = {q[u][3].x, q[u][3].y, q[u][3].z, q[u][3].w};
+        for (int j = 0; j < 8; ++j) top[j] = bot[j];
+      } else {
+        up_hlerp(base + y0 * rowpitch, x0c, x1c, hx, lx, top);
+      }
+      cy0 = y0;
+      cy1 = -1;
+    }
+    if (y1 != cy1) {
+      if (y1 == y0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bot[j] = top[j];
+      } else {
+        up_hlerp(base + y1 * rowpitch, x0c, x1c, hx, lx, bot);
+      }
+      cy1 = y1;
+    }
     uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float lo = hy * (hx * bf16_lo(av[j]) + lx * bf16_lo(bv[j])) + ly[u] * (hx * bf16_lo(cv[j]) + lx * bf16_lo(dv[j]));
-      const float hi = hy * (hx * bf16_hi(av[j]) + lx * bf16_hi(bv[j])) + ly[u] * (hx * bf16_hi(cv[j]) + lx * bf16_hi(dv[j]));
-      o[j] = pack_bf16x2(lo, hi);
-    }
-    __nv_bfloat16* dst = out + ((static_cast<long long>(b) * Ho + yo) * Wo + xo) * C + gi * 8;
+    for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(hy * top[2 * j] + ly * bot[2 * j], hy * top[2 * j + 1] + ly * bot[2 * j + 1]);
     *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    dst += static_cast<long long>(Wo) * C;
   }
 }
 

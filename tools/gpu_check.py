@@ -235,10 +235,10 @@ def chk_channel_ln(C):
     return _cmp("cln", out, ref, 2e-2, 1e-2)
 
 
-def chk_upsample(Hi, Ho):
+def chk_upsample(Hi, Ho, C=64):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(8)
-    x = torch.randn(2, Hi, Hi, 64, generator=g, device="cuda").bfloat16()
+    x = torch.randn(2, Hi, Hi, C, generator=g, device="cuda").bfloat16()
     out = ops.upsample(x, Ho, Ho)
     torch.cuda.synchronize()
     ref = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), (Ho, Ho), mode="bilinear", align_corners=True)
@@ -370,6 +370,11 @@ CHECKS = {
     "channel_ln_1024": lambda: chk_channel_ln(1024),
     "upsample_19_37": lambda: chk_upsample(19, 37),
     "upsample_37_74": lambda: chk_upsample(37, 74),
+    "upsample_148_296_c256": lambda: chk_upsample(148, 296, 256),
+    "upsample_40_70_c128": lambda: chk_upsample(40, 70, 128),   # not a 2x map: strips cross source rows irregularly
+    "channel_ln_256": lambda: chk_channel_ln(256),
+    "channel_ln_512": lambda: chk_channel_ln(512),
+    "channel_ln_1536": lambda: chk_channel_ln(1536),
     "fused_tail_5x7": lambda: chk_fused_tail(5, 7),
     "fused_tail_9x9": lambda: chk_fused_tail(9, 9),
     "patch_gather": chk_patch_gather,
