@@ -25,6 +25,7 @@
 #include "postproc.cuh"
 #include "evalops.cuh"
 #include "gemm.cuh"
+#include "pack.cuh"
 #include "tma_host.h"
 
 namespace ada {
@@ -47,14 +48,6 @@ struct AdaError : std::runtime_error {
   } while (0)
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static inline uint16_t f2bf(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn for finite values
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>(u >> 16);
-}
-
 // ------------------------------------------------------------------------------------------------ device context
 // Everything that CUDA keeps per device (SM count, the opt-in shared-memory size of each kernel) is keyed by the device
 // ordinal that is current on the calling thread: one process may drive several GPUs, one handle each (SURVEY.md section 5,
@@ -264,6 +257,33 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
       if (want != 2) ok = pairs >= 2 * (device_info().sms / 2);
     }
     if (ok && want != 1) cg = 2;
+  }
+  // ---- small linear problems: wave quantisation. The rules above pick the widest tile; at M = 5480 (ViT-L, four images:
+  // the per-GPU share of the batch-32 configuration on eight GPUs) a [M, 1024] output is 172 128x256 tiles on 148 SMs --
+  // two waves, the second one 16 % full (fc2: 846 TFLOP/s, proj: 509). Choose the tile by modelled time = waves x tile
+  // width / relative tile efficiency instead (efficiencies from the per-signature timings in profiles/README.md). The
+  // accumulation order of an output element does not depend on the tile shape, so results stay bit-identical.
+  if (!L.force_bn && !L.force_cg && L.a_mode == A_LINEAR && (epi_is_bf16(g.epi) || g.epi == EPI_SWIGLU) && L.K > 256) {
+    static const int tile_model = env_int("ADA_GEMM_TILE_MODEL", 1);
+    const int sms = device_info().sms;
+    const long long units_now = static_cast<long long>((L.M + kBlockM * cg - 1) / (kBlockM * cg)) * ((L.N + bn - 1) / bn);
+    if (tile_model && units_now < 6LL * (sms / cg)) {  // large grids keep the established choice
+      struct Cand { int bn, cg; double eff; };
+      const Cand cands[4] = {{256, 2, 1.00}, {256, 1, 0.88}, {128, 1, 0.72}, {64, 1, 0.45}};
+      double best = 1e30;
+      for (const Cand& c : cands) {
+        if (g.epi == EPI_SWIGLU && c.bn < 128) continue;
+        if (c.bn > 64 && (L.N + c.bn - 1) / c.bn * c.bn > L.N + L.N / 8 + 63) continue;  // too much column padding
+        const long long tiles = static_cast<long long>((L.M + kBlockM * c.cg - 1) / (kBlockM * c.cg)) * ((L.N + c.bn - 1) / c.bn);
+        const long long units = sms / c.cg;
+        const double t = static_cast<double>((tiles + units - 1) / units) * c.bn / c.eff;
+        if (t < best * 0.999) {
+          best = t;
+          bn = c.bn;
+          cg = c.cg;
+        }
+      }
+    }
   }
   CUtensorMap ta, tb;
   int tiles_m;
@@ -618,39 +638,6 @@ static void launch_im2col_s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B,
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// conv3x3 weight [Cout, Cin, 3, 3] (torch) -> [Cout, 9 * Cpad], K index = tap*Cpad + ci, zero padded channels.
-static std::vector<uint16_t> pack_conv3x3_host(const float* w, int Cout, int Cin) {
-  const int Cpad = round_up(Cin, kBlockK);
-  std::vector<uint16_t> o(static_cast<size_t>(Cout) * 9 * Cpad, 0);
-  for (int co = 0; co < Cout; ++co)
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int t = 0; t < 9; ++t)
-        o[(static_cast<size_t>(co) * 9 + t) * Cpad + ci] = f2bf(w[(static_cast<size_t>(co) * Cin + ci) * 9 + t]);
-  return o;
-}
-// ConvTranspose2d weight [Cin, Cout, ks, ks] with stride == ks -> [(ky*ks+kx)*Cout + co, Cin]
-static std::vector<uint16_t> pack_convT_host(const float* w, int Cin, int Cout, int ks) {
-  std::vector<uint16_t> o(static_cast<size_t>(ks) * ks * Cout * Cin);
-  for (int ci = 0; ci < Cin; ++ci)
-    for (int co = 0; co < Cout; ++co)
-      for (int kk = 0; kk < ks * ks; ++kk)
-        o[(static_cast<size_t>(kk) * Cout + co) * Cin + ci] = f2bf(w[(static_cast<size_t>(ci) * Cout + co) * ks * ks + kk]);
-  return o;
-}
-// output_conv2.0 weight [32, Cm, 3, 3] -> per-tap 1x1 contractions [(tap*32 + co), Cm] for the fused tail
-static std::vector<uint16_t> pack_tail_taps_host(const float* w, int Cm) {
-  std::vector<uint16_t> o(static_cast<size_t>(288) * Cm);
-  for (int co = 0; co < 32; ++co)
-    for (int ci = 0; ci < Cm; ++ci)
-      for (int t = 0; t < 9; ++t) o[(static_cast<size_t>(t) * 32 + co) * Cm + ci] = f2bf(w[(static_cast<size_t>(co) * Cm + ci) * 9 + t]);
-  return o;
-}
-static std::vector<uint16_t> to_bf16_host(const float* w, size_t n) {
-  std::vector<uint16_t> o(n);
-  for (size_t i = 0; i < n; ++i) o[i] = f2bf(w[i]);
-  return o;
-}
-
 // Bicubic resampling of the position table, mirroring ATen upsample_bicubic2d (align_corners=False, A=-0.75) called
 // with an explicit scale_factor: src = (dst + 0.5) / scale_factor - 0.5, taps clamped to the border.
 static void cubic_coeffs(float t, float c[4]) {
@@ -694,10 +681,13 @@ static void interp_pos_host(const float* pos, int grid, int D, int gh, int gw, f
 }
 
 // ------------------------------------------------------------------------------------------------ model
-struct HostTensor {
-  std::vector<float> data;
+// One state-dict tensor between ada_set_weight and ada_finalize: fp32, staged where it arrived -- a device copy for device
+// sources (no PCIe round trip), a host copy for host sources (works without a device; uploaded by ada_finalize).
+struct StagedTensor {
+  std::vector<float> host;
+  float* dev = nullptr;
   std::vector<int64_t> shape;
-  size_t numel() const { return data.size(); }
+  size_t n = 0;
 };
 
 struct DevBuf {
@@ -730,7 +720,7 @@ struct ada_model {
   ada_config cfg{};
   int device = -1;  // device ordinal current at ada_create: weights, workspace and every launch live there
   std::map<std::string, std::vector<int64_t>> spec;  // expected state dict: name -> shape (expected_weights)
-  std::unordered_map<std::string, HostTensor> host;  // raw fp32 state dict (released after finalize)
+  std::unordered_map<std::string, StagedTensor> host;  // staged fp32 state dict (released by ada_finalize)
   bool finalized = false;
   bool capture = false;
   bool profile = false;
@@ -807,8 +797,15 @@ struct ada_model {
     graph_state = 0;
   }
 
+  void drop_staged() {
+    for (auto& kv : host)
+      if (kv.second.dev) cudaFree(kv.second.dev);
+    host.clear();
+  }
+
   ~ada_model() {
     drop_graph();
+    drop_staged();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     for (void* p : owned) cudaFree(p);
     if (arena.p) cudaFree(arena.p);
@@ -829,32 +826,73 @@ static T* upload(ada_model* m, const void* src, size_t bytes) {
   m->owned.push_back(d);
   return reinterpret_cast<T*>(d);
 }
-static const HostTensor& need(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
+template <typename T>
+static T* dev_alloc(ada_model* m, size_t elems) {
+  void* d = nullptr;
+  ADA_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(elems * sizeof(T), 16)));
+  m->owned.push_back(d);
+  return reinterpret_cast<T*>(d);
+}
+// staged tensor -> device fp32 pointer (shape checked); host-staged tensors are uploaded on first use
+static const float* need(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
   auto it = m->host.find(key);
   if (it == m->host.end()) throw AdaError(ADA_ESTATE, "missing weight: " + key);
-  if (it->second.shape != shape) {
+  StagedTensor& t = it->second;
+  if (t.shape != shape) {
     std::string s = "shape mismatch for " + key + ": got [";
-    for (auto v : it->second.shape) s += std::to_string(v) + ",";
+    for (auto v : t.shape) s += std::to_string(v) + ",";
     s += "] expected [";
     for (auto v : shape) s += std::to_string(v) + ",";
     throw AdaError(ADA_EINVAL, s + "]");
   }
-  return it->second;
+  if (!t.dev) {
+    ADA_CHECK_CUDA(cudaMalloc(&t.dev, std::max<size_t>(t.n * 4, 16)));
+    ADA_CHECK_CUDA(cudaMemcpy(t.dev, t.host.data(), t.n * 4, cudaMemcpyHostToDevice));
+    std::vector<float>().swap(t.host);
+  }
+  return t.dev;
+}
+static size_t numel_of(const std::vector<int64_t>& shape) {
+  size_t n = 1;
+  for (auto v : shape) n *= static_cast<size_t>(v);
+  return n;
+}
+// small tensors the host needs (position table, cls token, patch-embed biases)
+static std::vector<float> need_host(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
+  const float* d = need(m, key, shape);
+  std::vector<float> h(numel_of(shape));
+  ADA_CHECK_CUDA(cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost));
+  return h;
+}
+static void run_pack(const float* src, const float* src2, __nv_bfloat16* dst, long long n, const PackDesc& d) {
+  pack_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(src, src2, dst, n, d);
+  ADA_CHECK_CUDA(cudaGetLastError());
 }
 static float* up_f32(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
-  const HostTensor& t = need(m, key, shape);
-  return upload<float>(m, t.data.data(), t.numel() * 4);
+  const float* src = need(m, key, shape);
+  const size_t n = numel_of(shape);
+  float* d = dev_alloc<float>(m, n);
+  ADA_CHECK_CUDA(cudaMemcpyAsync(d, src, n * 4, cudaMemcpyDeviceToDevice, nullptr));
+  return d;
 }
 static __nv_bfloat16* up_bf16(ada_model* m, const std::string& key, std::vector<int64_t> shape) {
-  const HostTensor& t = need(m, key, shape);
-  std::vector<uint16_t> h = to_bf16_host(t.data.data(), t.numel());
-  return upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+  const float* src = need(m, key, shape);
+  const size_t n = numel_of(shape);
+  __nv_bfloat16* d = dev_alloc<__nv_bfloat16>(m, n);
+  run_pack(src, nullptr, d, static_cast<long long>(n), PackDesc{PACK_CAST, 0, 0, 0, 0});
+  return d;
+}
+// conv3x3 weight [Cout, Cin, 3, 3] (torch) -> [Cout, 9 * Cpad], K index = tap*Cpad + ci, zero padded channels
+static __nv_bfloat16* pack_conv3x3_dev(ada_model* m, const float* src, int cout, int cin) {
+  const int Cpad = round_up(cin, kBlockK);
+  const long long n = static_cast<long long>(cout) * 9 * Cpad;
+  __nv_bfloat16* d = dev_alloc<__nv_bfloat16>(m, n);
+  run_pack(src, nullptr, d, n, PackDesc{PACK_CONV3X3, cout, cin, Cpad, 0});
+  return d;
 }
 static ConvW up_conv3x3(ada_model* m, const std::string& prefix, int cout, int cin, bool bias) {
-  const HostTensor& t = need(m, prefix + ".weight", {cout, cin, 3, 3});
-  std::vector<uint16_t> h = pack_conv3x3_host(t.data.data(), cout, cin);
   ConvW c;
-  c.w = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+  c.w = pack_conv3x3_dev(m, need(m, prefix + ".weight", {cout, cin, 3, 3}), cout, cin);
   c.cin = cin;
   c.cout = cout;
   c.ldw = 9 * round_up(cin, kBlockK);
@@ -957,25 +995,20 @@ static void finalize_model(ada_model* m) {
   m->cin_total = 3 + Cg;
   m->kpad = round_up(m->cin_total * 196, kBlockK);
   {
-    const HostTensor& wr = need(m, pre + "patch_embed.proj.weight", {D, 3, 14, 14});
-    const HostTensor& br = need(m, pre + "patch_embed.proj.bias", {D});
-    std::vector<uint16_t> w(static_cast<size_t>(D) * m->kpad, 0);
-    m->embed_bias.assign(br.data.begin(), br.data.end());
-    for (int d = 0; d < D; ++d)
-      for (int k = 0; k < 3 * 196; ++k) w[static_cast<size_t>(d) * m->kpad + k] = f2bf(wr.data[static_cast<size_t>(d) * 588 + k]);
+    const float* wr = need(m, pre + "patch_embed.proj.weight", {D, 3, 14, 14});
+    m->embed_bias = need_host(m, pre + "patch_embed.proj.bias", {D});
+    const float* wg = nullptr;
     if (Cg > 0) {
-      const HostTensor& wg = need(m, pre + "patch_embed_guidance.proj.weight", {D, Cg, 14, 14});
-      const HostTensor& bg = need(m, pre + "patch_embed_guidance.proj.bias", {D});
-      for (int d = 0; d < D; ++d) {
-        for (int k = 0; k < Cg * 196; ++k)
-          w[static_cast<size_t>(d) * m->kpad + 588 + k] = f2bf(wg.data[static_cast<size_t>(d) * Cg * 196 + k]);
-        m->embed_bias[d] += bg.data[d];
-      }
+      wg = need(m, pre + "patch_embed_guidance.proj.weight", {D, Cg, 14, 14});
+      const std::vector<float> bg = need_host(m, pre + "patch_embed_guidance.proj.bias", {D});
+      for (int d = 0; d < D; ++d) m->embed_bias[d] += bg[d];
     }
-    m->w_embed = upload<__nv_bfloat16>(m, w.data(), w.size() * 2);
+    const long long n = static_cast<long long>(D) * m->kpad;
+    m->w_embed = dev_alloc<__nv_bfloat16>(m, n);
+    run_pack(wr, wg, m->w_embed, n, PackDesc{PACK_EMBED, D, Cg, m->kpad, 0});
   }
-  m->pos_host = need(m, pre + "pos_embed", {1, 1 + G * G, D}).data;
-  m->cls_host = need(m, pre + "cls_token", {1, 1, D}).data;
+  m->pos_host = need_host(m, pre + "pos_embed", {1, 1 + G * G, D});
+  m->cls_host = need_host(m, pre + "cls_token", {1, 1, D});
   need(m, pre + "mask_token", {1, D});  // dead weight, must exist for strict loading (dinov2.py:188)
   // ---- blocks
   m->blocks.resize(c.depth);
@@ -1001,18 +1034,14 @@ static void finalize_model(ada_model* m) {
     } else {
       // SwiGLU: interleave x1 / x2 rows in 32-wide chunks so one accumulator tile holds both halves (swiglu_ffn.py:30-32)
       const int Hd = c.ffn_hidden;
-      const HostTensor& w12 = need(m, b + "mlp.w12.weight", {2 * Hd, D});
-      const HostTensor& b12 = need(m, b + "mlp.w12.bias", {2 * Hd});
-      std::vector<uint16_t> wi(static_cast<size_t>(2) * Hd * D);
-      std::vector<float> bi(2 * Hd);
-      for (int r = 0; r < 2 * Hd; ++r) {
-        const int chunk = r / 64, within = r % 64;
-        const int srow = (within < 32) ? chunk * 32 + within : Hd + chunk * 32 + (within - 32);
-        bi[r] = b12.data[srow];
-        for (int k = 0; k < D; ++k) wi[static_cast<size_t>(r) * D + k] = f2bf(w12.data[static_cast<size_t>(srow) * D + k]);
-      }
-      w.w1 = upload<__nv_bfloat16>(m, wi.data(), wi.size() * 2);
-      w.b1 = upload<float>(m, bi.data(), bi.size() * 4);
+      const float* w12 = need(m, b + "mlp.w12.weight", {2 * Hd, D});
+      const float* b12 = need(m, b + "mlp.w12.bias", {2 * Hd});
+      const long long n = 2LL * Hd * D;
+      w.w1 = dev_alloc<__nv_bfloat16>(m, n);
+      run_pack(w12, nullptr, w.w1, n, PackDesc{PACK_SWIGLU, Hd, D, 0, 0});
+      w.b1 = dev_alloc<float>(m, 2 * Hd);
+      swiglu_bias_kernel<<<(2 * Hd + 255) / 256, 256>>>(b12, w.b1, Hd);
+      ADA_CHECK_CUDA(cudaGetLastError());
       w.w2 = up_bf16(m, b + "mlp.w3.weight", {D, Hd});
       w.b2 = up_f32(m, b + "mlp.w3.bias", {D});
     }
@@ -1029,15 +1058,14 @@ static void finalize_model(ada_model* m) {
     m->b_proj[i] = up_f32(m, hd + "projects." + si + ".bias", {Ci});
     if (i == 0 || i == 1) {
       const int ks = (i == 0) ? 4 : 2;
-      const HostTensor& t = need(m, hd + "resize_layers." + si + ".weight", {Ci, Ci, ks, ks});
-      std::vector<uint16_t> h = pack_convT_host(t.data.data(), Ci, Ci, ks);
-      m->w_rs[i] = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+      const float* t = need(m, hd + "resize_layers." + si + ".weight", {Ci, Ci, ks, ks});
+      const long long n = static_cast<long long>(ks) * ks * Ci * Ci;
+      m->w_rs[i] = dev_alloc<__nv_bfloat16>(m, n);
+      run_pack(t, nullptr, m->w_rs[i], n, PackDesc{PACK_CONVT, Ci, Ci, ks, 0});
       m->b_rs[i] = up_f32(m, hd + "resize_layers." + si + ".bias", {Ci});
     } else if (i == 3) {
-      const HostTensor& t = need(m, hd + "resize_layers.3.weight", {Ci, Ci, 3, 3});
       ADA_REQUIRE(Ci % kBlockK == 0, "resize_layers.3 expects C % 64 == 0");
-      std::vector<uint16_t> h = pack_conv3x3_host(t.data.data(), Ci, Ci);
-      m->w_rs[i] = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+      m->w_rs[i] = pack_conv3x3_dev(m, need(m, hd + "resize_layers.3.weight", {Ci, Ci, 3, 3}), Ci, Ci);
       m->b_rs[i] = up_f32(m, hd + "resize_layers.3.bias", {Ci});
     }
     if (c.input_projection) {
@@ -1059,20 +1087,22 @@ static void finalize_model(ada_model* m) {
   }
   m->oc1 = up_conv3x3(m, hd + "scratch.output_conv1", F / 2, F, true);
   {
-    const HostTensor& t = need(m, hd + "scratch.output_conv2.0.weight", {32, F / 2, 3, 3});
-    std::vector<uint16_t> h = pack_tail_taps_host(t.data.data(), F / 2);
-    m->w_tail_taps = upload<__nv_bfloat16>(m, h.data(), h.size() * 2);
+    const float* t = need(m, hd + "scratch.output_conv2.0.weight", {32, F / 2, 3, 3});
+    const long long n = 288LL * (F / 2);
+    m->w_tail_taps = dev_alloc<__nv_bfloat16>(m, n);
+    run_pack(t, nullptr, m->w_tail_taps, n, PackDesc{PACK_TAIL, F / 2, 0, 0, 0});
   }
   m->oc2 = up_conv3x3(m, hd + "scratch.output_conv2.0", 32, F / 2, true);
   {
-    const HostTensor& w2 = need(m, hd + "scratch.output_conv2.2.weight", {1, 32, 1, 1});
-    const HostTensor& b2 = need(m, hd + "scratch.output_conv2.2.bias", {1});
+    const std::vector<float> w2 = need_host(m, hd + "scratch.output_conv2.2.weight", {1, 32, 1, 1});
+    const std::vector<float> b2 = need_host(m, hd + "scratch.output_conv2.2.bias", {1});
     float aux[33];
-    for (int i = 0; i < 32; ++i) aux[i] = w2.data[i];
-    aux[32] = b2.data[0];
+    for (int i = 0; i < 32; ++i) aux[i] = w2[i];
+    aux[32] = b2[0];
     m->tail_aux = upload<float>(m, aux, sizeof(aux));
   }
-  m->host.clear();
+  ADA_CHECK_CUDA(cudaDeviceSynchronize());  // the pack kernels read the staged tensors released next
+  m->drop_staged();
   m->finalized = true;
 }
 
@@ -1223,8 +1253,9 @@ static void ensure_workspace(ada_model* m, int B, int H, int W, cudaStream_t st)
 
 // conv3x3 (pad 1, stride 1) over NHWC bf16 through the implicit-GEMM path
 static void conv3x3(const __nv_bfloat16* in, int B, int H, int W, const ConvW& cw, int act, const __nv_bfloat16* r1,
-                    const __nv_bfloat16* r2, __nv_bfloat16* out, __nv_bfloat16* out_relu, cudaStream_t st) {
+                    const __nv_bfloat16* r2, __nv_bfloat16* out, __nv_bfloat16* out_relu, cudaStream_t st, int force_cg = 0) {
   GemmLaunch L;
+  L.force_cg = force_cg;
   L.A = in;
   L.Bw = cw.w;
   L.M = B * H * W;
@@ -1453,7 +1484,8 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
     launch_upsample(m->ocb, m->path[k], B, hh, ww, ph[k], pw[k], F, st);
   }
   // output_conv1 -> bilinear to (H, W) -> output_conv2 (conv3x3 + ReLU + 1x1 + Sigmoid) (dpt.py:193-195)
-  conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st);
+  static const int oc1_cg = env_int("ADA_OC1_CG", 0);
+  conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st, oc1_cg);
   if (tail_fused(ph[1], pw[1], H, W)) {
     GemmArgs e{};
     e.epi = EPI_F16;  // the tap map is stored as fp16 (tail_gather_kernel interpolates it with packed fp16 FMAs)
@@ -1633,7 +1665,7 @@ int ada_set_weight(ada_handle h, const char* key, const float* data, const int64
     auto sp = h->spec.find(key);
     if (sp == h->spec.end())
       throw AdaError(ADA_EINVAL, std::string("ada_set_weight: unknown weight key for this architecture: ") + key);
-    HostTensor t;
+    StagedTensor t;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) {
       t.shape.push_back(shape[i]);
@@ -1646,15 +1678,20 @@ int ada_set_weight(ada_handle h, const char* key, const float* data, const int64
       for (auto v : sp->second) msg += std::to_string(v) + ",";
       throw AdaError(ADA_EINVAL, msg + "]");
     }
-    t.data.resize(n);
+    t.n = n;
     cudaPointerAttributes attr;
     bool on_device = false;
     if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice);
     cudaGetLastError();
-    if (on_device)
-      ADA_CHECK_CUDA(cudaMemcpy(t.data.data(), data, n * 4, cudaMemcpyDeviceToHost));
-    else
-      memcpy(t.data.data(), data, n * 4);
+    auto old = h->host.find(key);
+    if (old != h->host.end() && old->second.dev) cudaFree(old->second.dev);
+    if (on_device) {  // stays on the device: one device-to-device copy, packed by kernels in ada_finalize
+      ADA_CHECK_CUDA(cudaMalloc(&t.dev, std::max<size_t>(n * 4, 16)));
+      ADA_CHECK_CUDA(cudaMemcpyAsync(t.dev, data, n * 4, cudaMemcpyDeviceToDevice, nullptr));
+      ADA_CHECK_CUDA(cudaStreamSynchronize(nullptr));  // the caller may release `data` as soon as this returns
+    } else {
+      t.host.assign(data, data + n);
+    }
     h->host[key] = std::move(t);
   });
 }
@@ -1960,27 +1997,41 @@ int ada_op_tail_gather(const void* v_f16, const float* bias2, const float* aux, 
   });
 }
 
+// Weight packers for the operator-level tests: host fp32 in, device bf16 out -- through the same device kernels
+// (csrc/pack.cuh) ada_finalize uses.
+static void pack_from_host(const float* w_host, size_t n_in, void* dst, long long n_out, const PackDesc& d) {
+  require_device();
+  ADA_REQUIRE(w_host && dst, "null argument");
+  float* tmp = nullptr;
+  ADA_CHECK_CUDA(cudaMalloc(&tmp, n_in * 4));
+  cudaError_t e = cudaMemcpy(tmp, w_host, n_in * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    pack_weights_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256>>>(tmp, nullptr, static_cast<__nv_bfloat16*>(dst), n_out, d);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  cudaFree(tmp);
+  ADA_CHECK_CUDA(e);
+}
+
 int ada_pack_tail_taps(const float* w_host, int32_t Cm, void* dst) {
   return guarded([&] {
-    require_device();
-    std::vector<uint16_t> h = pack_tail_taps_host(w_host, Cm);
-    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    pack_from_host(w_host, static_cast<size_t>(32) * Cm * 9, dst, 288LL * Cm, PackDesc{PACK_TAIL, Cm, 0, 0, 0});
   });
 }
 
 int ada_pack_conv3x3(const float* w_host, int32_t Cout, int32_t Cin, void* dst) {
   return guarded([&] {
-    require_device();
-    std::vector<uint16_t> h = pack_conv3x3_host(w_host, Cout, Cin);
-    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    const int Cpad = round_up(Cin, kBlockK);
+    pack_from_host(w_host, static_cast<size_t>(Cout) * Cin * 9, dst, static_cast<long long>(Cout) * 9 * Cpad,
+                   PackDesc{PACK_CONV3X3, Cout, Cin, Cpad, 0});
   });
 }
 
 int ada_pack_convT(const float* w_host, int32_t Cin, int32_t Cout, int32_t ks, void* dst) {
   return guarded([&] {
-    require_device();
-    std::vector<uint16_t> h = pack_convT_host(w_host, Cin, Cout, ks);
-    ADA_CHECK_CUDA(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    pack_from_host(w_host, static_cast<size_t>(Cin) * Cout * ks * ks, dst, static_cast<long long>(ks) * ks * Cout * Cin,
+                   PackDesc{PACK_CONVT, Cin, Cout, ks, 0});
   });
 }
 

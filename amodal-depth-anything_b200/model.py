@@ -193,7 +193,11 @@ class _NativeModel(nn.Module):
         cfg.input_projection = c["input_projection"]
         cfg.normalize_input = c["normalize_input"]
         h = ctypes.c_void_p()
-        with torch.cuda.device(device):
+        # Weights go device -> device: ada_set_weight copies each tensor into the handle's staging memory on the legacy
+        # default stream and ada_finalize packs them with kernels (csrc/pack.cuh). Any dtype conversion below therefore runs
+        # on the default stream too, after whatever the caller's current stream has produced.
+        torch.cuda.current_stream(device).synchronize()
+        with torch.cuda.device(device), torch.cuda.stream(torch.cuda.default_stream(device)):
             L.check(lib.ada_create(ctypes.byref(cfg), ctypes.byref(h)))
             try:
                 for key, p in self._native_state().items():
