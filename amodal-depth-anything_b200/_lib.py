@@ -74,6 +74,7 @@ class GemmDesc(ctypes.Structure):
         ("sigmoid", c_int32),
         ("force_bn", c_int32),
         ("force_cg", c_int32),
+        ("conv_stride", c_int32),
     ]
 
 
@@ -112,7 +113,6 @@ SIGNATURES = {
     "ada_op_upsample": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ada_op_patch_gather": (c_int32, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int32, c_int32,
                                       c_int32, c_int32, c_void_p]),
-    "ada_op_im2col_s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ada_op_tail_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]),
     "ada_pack_tail_taps": (c_int32, [c_void_p, c_int32, c_void_p]),

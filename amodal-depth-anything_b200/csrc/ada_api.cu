@@ -188,7 +188,8 @@ struct GemmLaunch {
   const void* Bw = nullptr;  // [N, K] pitch ldb
   int M = 0, N = 0, K = 0, lda = 0, ldb = 0;
   int a_mode = A_LINEAR;
-  int batch = 0, H = 0, W = 0, Cin = 0;
+  int batch = 0, H = 0, W = 0, Cin = 0;  // conv: OUTPUT map size
+  int conv_stride = 1, Hin = 0, Win = 0;  // conv: stride 1 or 2 and the input map size (0 = same as output)
   GemmArgs args{};           // epilogue fields filled by caller
   __nv_bfloat16* out_relu = nullptr;  // EPI_BF16: optional relu(out) copy (second TMA store map)
   int force_bn = 0;
@@ -295,12 +296,18 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     g.tiles_y = (L.H + kTileH - 1) / kTileH;
     g.c_chunks = round_up(L.Cin, kBlockK) / kBlockK;
     g.K = 9 * g.c_chunks * kBlockK;
-    uint64_t dims[4] = {static_cast<uint64_t>(L.Cin), static_cast<uint64_t>(L.W), static_cast<uint64_t>(L.H),
+    const int sd = L.conv_stride;
+    ADA_REQUIRE(sd == 1 || sd == 2, "conv stride is 1 or 2");
+    const int Hin = L.Hin ? L.Hin : L.H, Win = L.Win ? L.Win : L.W;
+    ADA_REQUIRE((Hin - 1) / sd + 1 == L.H && (Win - 1) / sd + 1 == L.W, "conv input / output size mismatch (k3, pad 1)");
+    g.conv_stride = sd;
+    uint64_t dims[4] = {static_cast<uint64_t>(L.Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                         static_cast<uint64_t>(L.batch)};
-    uint64_t str[3] = {static_cast<uint64_t>(L.Cin) * 2, static_cast<uint64_t>(L.W) * L.Cin * 2,
-                       static_cast<uint64_t>(L.H) * L.W * L.Cin * 2};
-    uint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
-    ta = make_tmap_bf16(L.A, 4, dims, str, box);
+    uint64_t str[3] = {static_cast<uint64_t>(L.Cin) * 2, static_cast<uint64_t>(Win) * L.Cin * 2,
+                       static_cast<uint64_t>(Hin) * Win * L.Cin * 2};
+    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(kTileW * sd), static_cast<uint32_t>(kTileH * sd), 1};
+    uint32_t es[4] = {1, static_cast<uint32_t>(sd), static_cast<uint32_t>(sd), 1};
+    ta = make_tmap_bf16(L.A, 4, dims, str, box, es);
     tiles_m = L.batch * g.tiles_x * g.tiles_y;
     ADA_REQUIRE(L.M == L.batch * L.H * L.W, "conv M mismatch");
   } else {
@@ -628,15 +635,6 @@ static void launch_patch_gather(const float* rgb, const float* const* guides, co
   ++g_launches;
 }
 
-static void launch_im2col_s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t st) {
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
-  ProfScope prof(PC_GATHER, 0.0, 4.0 * total * 8, st);
-  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, B, H, W, C, Ho, Wo);
-  ADA_CHECK_CUDA(cudaGetLastError());
-  ++g_launches;
-}
-
 // ------------------------------------------------------------------------------------------------ weight packing
 // Bicubic resampling of the position table, mirroring ATen upsample_bicubic2d (align_corners=False, A=-0.75) called
 // with an explicit scale_factor: src = (dst + 0.5) / scale_factor - 0.5, taps clamped to the border.
@@ -764,7 +762,7 @@ struct ada_model {
   __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *ybuf = nullptr, *ybuf2 = nullptr, *a_embed = nullptr;
   __nv_bfloat16* tap[4] = {};
   float* tokens_dbg = nullptr;
-  __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *col4 = nullptr, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
+  __nv_bfloat16 *proj[4] = {}, *rs[4] = {}, *ipb[4] = {}, *rnb[4] = {}, *rnr[4] = {};
   __nv_bfloat16 *t1 = nullptr, *sum = nullptr, *sumr = nullptr, *r2 = nullptr, *ocb = nullptr, *path[5] = {},
                 *oc1b = nullptr, *up = nullptr, *vtap = nullptr;
   int last_B = 0, last_H = 0, last_W = 0, last_launches = 0;
@@ -1202,7 +1200,6 @@ static size_t plan_workspace(ada_model* m, int B, int H, int W, bool dry, char* 
     reg("layer" + std::to_string(i + 1) + "_rn", m->rnb[i], pix * F, 0);
     reg("layer" + std::to_string(i + 1), m->ipb[i], pix * Ci, 0);
   }
-  m->col4 = b.take<__nv_bfloat16>(static_cast<size_t>(B) * sh[3] * sw[3] * 9 * c.out_channels[3]);
   m->t1 = b.take<__nv_bfloat16>(maxpix * F);
   m->sum = b.take<__nv_bfloat16>(maxpix * F);
   m->sumr = b.take<__nv_bfloat16>(maxpix * F);
@@ -1437,14 +1434,26 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
       e.ks = ks;
       e.cout = Ci;
       linear(m->proj[i], BP, Ci, Ci, m->w_rs[i], ks * ks * Ci, Ci, e, st);
-    } else if (i == 3) {  // conv 3x3 stride 2 (dpt.py:102-107): gather + GEMM
-      launch_im2col_s2(m->proj[3], m->col4, B, gh, gw, Ci, st);
-      GemmArgs e{};
-      e.epi = EPI_BF16;
-      e.bias = m->b_rs[3];
-      e.out_bf16 = m->rs[3];
-      e.ldo = Ci;
-      linear(m->col4, B * sh[3] * sw[3], 9 * Ci, 9 * Ci, m->w_rs[3], Ci, 9 * Ci, e, st);
+    } else if (i == 3) {  // conv 3x3 stride 2 (dpt.py:102-107): implicit GEMM, the tensor map walks the input with stride 2
+      GemmLaunch L;
+      L.A = m->proj[3];
+      L.Bw = m->w_rs[3];
+      L.M = B * sh[3] * sw[3];
+      L.N = Ci;
+      L.ldb = 9 * round_up(Ci, kBlockK);
+      L.a_mode = A_CONV3X3;
+      L.batch = B;
+      L.H = sh[3];
+      L.W = sw[3];
+      L.Hin = gh;
+      L.Win = gw;
+      L.conv_stride = 2;
+      L.Cin = Ci;
+      L.args.epi = EPI_BF16;
+      L.args.bias = m->b_rs[3];
+      L.args.out_bf16 = m->rs[3];
+      L.args.ldo = Ci;
+      launch_gemm(L, st);
     }
     if (c.input_projection) {  // input_projection[i]: conv3x3 + channel LN + ReLU (dpt.py:153-159,178-179)
       conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
@@ -1721,7 +1730,7 @@ int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W) {
   const ada_config& c = h->cfg;
   // gather + cls + embed | per block: 2 LN + 4 GEMM + attention | 4 tap LN | head
   int n = 3 + c.depth * 7 + 4;
-  n += 4 /*projects*/ + 2 /*convT*/ + 2 /*im2col+gemm*/ + 4 * (c.input_projection ? 3 : 1) /*ip conv, LN, rn*/;
+  n += 4 /*projects*/ + 2 /*convT*/ + 1 /*stride-2 conv*/ + 4 * (c.input_projection ? 3 : 1) /*ip conv, LN, rn*/;
   n += 3 * 6 + 4 /*refinenets: (2+2+1+1) x3, (2+1+1) for #4*/;
   n += 3 /*oc1, upsample, tail*/;
   if (h->capture) n += 0;
@@ -1844,6 +1853,14 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     L.Cin = d->Cin;
     L.force_bn = d->force_bn;
     L.force_cg = d->force_cg;
+    if (d->a_mode == A_CONV3X3 && d->conv_stride == 2) {  // H, W of the descriptor are the INPUT map
+      L.conv_stride = 2;
+      L.Hin = d->H;
+      L.Win = d->W;
+      L.H = (d->H - 1) / 2 + 1;
+      L.W = (d->W - 1) / 2 + 1;
+      L.M = d->batch * L.H * L.W;
+    }
     GemmArgs& e = L.args;
     e.epi = d->epi;
     e.act = d->act;
@@ -1977,14 +1994,6 @@ int ada_op_patch_gather(const float* rgb, const float* const* guides, const int3
     require_device();
     launch_patch_gather(rgb, guides, guide_ch, n_guides, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, Kpad, 1,
                         static_cast<cudaStream_t>(stream));
-  });
-}
-
-int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
-  return guarded([&] {
-    require_device();
-    launch_im2col_s2(static_cast<const __nv_bfloat16*>(in_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, H, W, C,
-                     static_cast<cudaStream_t>(stream));
   });
 }
 

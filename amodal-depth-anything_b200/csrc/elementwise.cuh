@@ -1,4 +1,4 @@
-// Bandwidth-bound kernels of the path: LayerNorm (token and channel), patch gather, cls rows, stride-2 im2col,
+// Bandwidth-bound kernels of the path: LayerNorm (token and channel), patch gather, cls rows,
 // bilinear (align_corners=True) upsampling. All vectorised to 16-byte accesses, fp32 statistics.
 #pragma once
 #include "ptx.cuh"
@@ -217,28 +217,6 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls_pos, float* __rest
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
   x[static_cast<long long>(b) * n_tok * D + d] = cls_pos[d];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Stride-2 3x3 pad-1 gather (resize_layers[3], dpt.py:102-107): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C], tap-major K.
-__global__ void __launch_bounds__(256)
-im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
-                 int Ho, int Wo) {
-  const int groups = C >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * groups;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gi = static_cast<int>(idx % groups);
-  long long t = idx / groups;
-  const int tap = static_cast<int>(t % 9); t /= 9;
-  const int xo = static_cast<int>(t % Wo); t /= Wo;
-  const int yo = static_cast<int>(t % Ho);
-  const int b = static_cast<int>(t / Ho);
-  const int y = yo * 2 + tap / 3 - 1, x = xo * 2 + tap % 3 - 1;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (y >= 0 && y < H && x >= 0 && x < W)
-    v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * C + gi * 8);
-  *reinterpret_cast<uint4*>(out + idx * 8) = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -19,8 +19,9 @@
 // tcgen05.commit multicasts `empty` / `tmem-full` to both CTAs, both epilogues release the leader's `tmem-empty`.
 //
 // The A operand is fetched either as a plain row-major matrix (linear layers, 1x1 convs, transposed convs with k == s)
-// or as an implicit-GEMM 3x3/pad-1/stride-1 convolution over an NHWC map: the M tile is an 8x16 pixel patch and each
-// of the 9 taps is one shifted 4-D TMA box whose out-of-bounds part the hardware zero-fills (that is the padding).
+// or as an implicit-GEMM 3x3/pad-1 convolution (stride 1 or 2) over an NHWC map: the M tile is an 8x16 patch of OUTPUT
+// pixels and each of the 9 taps is one shifted 4-D TMA box whose out-of-bounds part the hardware zero-fills (that is the
+// padding); for stride 2 the tensor map traverses the input with element stride 2 in x and y.
 //
 // Epilogue data path. After tcgen05.ld each thread owns one accumulator row; storing that straight to global touches
 // 32 different cache lines per warp instruction (measured: 32 sectors/request, K=1024 GEMMs ran epilogue-bound at
@@ -81,7 +82,8 @@ struct GemmArgs {
   int a_mode;
   int epi, act;
   // conv geometry (A_CONV3X3) -- also used by EPI_CONVT for the input grid
-  int H, W, tiles_x, tiles_y, c_chunks;  // c_chunks = c_pad / 64
+  int H, W, tiles_x, tiles_y, c_chunks;  // OUTPUT map size; c_chunks = c_pad / 64
+  int conv_stride;      // A_CONV3X3: 1, or 2 (resize_layers[3], dpt.py:102-107): input pixel = stride * output pixel + tap - 1
   // epilogue operands
   const float* bias;        // [N] (EPI_CONVT: [Cout]) or nullptr
   const float* gamma;       // [N] LayerScale, or nullptr
@@ -261,14 +263,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
           mbar_expect_tx_cluster_w(fb, Cfg::kStageBytes);
           if (g.a_mode == A_CONV3X3)
-            tma_load_4d_cg2_w(sa, &tmap_a, fb, cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+            tma_load_4d_cg2_w(sa, &tmap_a, fb, cc * kBlockK, x0 * g.conv_stride + kx - 1, y0 * g.conv_stride + ky - 1, img);
           else
             tma_load_2d_cg2_w(sa, &tmap_a, fb, kb * kBlockK, m_row0);
           tma_load_2d_cg2_w(sb, &tmap_b, fb, kb * kBlockK, n_row0);
         } else {
           mbar_expect_tx_w(full_bar(stage), Cfg::kStageBytes);
           if (g.a_mode == A_CONV3X3)
-            tma_load_4d_w(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 + kx - 1, y0 + ky - 1, img);
+            tma_load_4d_w(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 * g.conv_stride + kx - 1, y0 * g.conv_stride + ky - 1, img);
           else
             tma_load_2d_w(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_row0);
           tma_load_2d_w(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_row0);

@@ -28,8 +28,10 @@ inline PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 // bf16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides in BYTES for dims 1..rank-1.
+// elem_strides (optional): traversal stride per dimension; a box of `box[i]` tensor elements then delivers
+// ceil(box[i] / elem_strides[i]) elements (every elem_strides[i]-th one) -- the stride-2 implicit-GEMM convolution.
 inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                  const uint32_t* box) {
+                                  const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   CUtensorMap m;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -38,7 +40,7 @@ inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* di
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),

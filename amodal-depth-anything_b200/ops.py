@@ -28,7 +28,7 @@ def _call(t, fn, *args):
 
 def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,
          out_relu=None, resid1=None, resid2=None, aux=None, ldo=0, P=0, ks=0, cout=0, sigmoid=0, force_bn=0,
-         force_cg=0, conv=None, N=None, K=None, M=None, H=0, W=0):
+         force_cg=0, conv=None, N=None, K=None, M=None, H=0, W=0, conv_stride=1):
     """A: bf16 [M,K] (linear) or NHWC bf16 [B,H,W,Cin] (conv=(B,H,W,Cin)); Wt: bf16 [N,Kw]."""
     lib = L.load()
     d = L.GemmDesc()
@@ -51,6 +51,7 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
         setattr(d, name, t.data_ptr() if t is not None else None)
     d.ldo, d.P, d.ks, d.cout, d.sigmoid, d.force_bn = ldo, P, ks, cout, sigmoid, force_bn
     d.force_cg = force_cg
+    d.conv_stride = conv_stride
     _call(A, lib.ada_op_gemm, ctypes.byref(d))
 
 
@@ -93,14 +94,6 @@ def patch_gather(rgb, guides, Kpad):
     ptrs = (ctypes.c_void_p * max(n, 1))(*[g.data_ptr() for g in guides])
     chs = (ctypes.c_int32 * max(n, 1))(*[g.shape[1] for g in guides])
     _call(rgb, L.load().ada_op_patch_gather, _p(rgb), ptrs, chs, n, _p(out), B, H, W, Kpad)
-    return out
-
-
-def im2col_s2(x_nhwc):
-    B, H, W, C = x_nhwc.shape
-    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    out = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device=x_nhwc.device)
-    _call(x_nhwc, L.load().ada_op_im2col_s2, _p(x_nhwc), _p(out), B, H, W, C)
     return out
 
 

@@ -88,7 +88,7 @@ int ada_set_graph(ada_handle h, int32_t on);
 /* Measurement hook (bench.py): when on, every kernel launch of ada_forward is bracketed by CUDA events on the launch
  * stream. ada_profile_read syncs, then sums per kernel class since the last read: elapsed ms, algorithmic FLOPs,
  * algorithmic bytes, launches. Classes: 0 tcgen05 GEMM (linear), 1 tcgen05 GEMM (implicit conv3x3), 2 attention,
- * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls / im2col), 7 fused tail
+ * 3 token LayerNorm, 4 channel LayerNorm+ReLU, 5 bilinear upsample, 6 gathers (patch / cls rows), 7 fused tail
  * gather. n_classes >= 8. */
 int ada_set_profile(ada_handle h, int32_t on);
 int ada_profile_read(ada_handle h, int32_t n_classes, double* ms, double* flops, double* bytes, int32_t* launches);
@@ -115,7 +115,7 @@ typedef struct ada_gemm_desc {
   const void* A;        /* bf16 [M,K] row-major (lda) or, conv mode, NHWC [B,H,W,Cin] */
   const void* Bw;       /* bf16 [N,K] row-major (ldb): the torch Linear / packed conv weight */
   int32_t M, N, K, lda, ldb;
-  int32_t a_mode;       /* 0 linear, 1 conv3x3 (pad 1, stride 1) */
+  int32_t a_mode;       /* 0 linear, 1 conv3x3 (pad 1; stride 1, or 2 with conv_stride) */
   int32_t epi, act;     /* see EpiMode / ActMode in csrc/gemm.cuh (0 bf16 out, 2 embed, 3 convT, 4 tail, 5 SwiGLU,
                            9 fp32 in-place residual: out_f32 += (acc + bias) * gamma, 10 = mode 0 stored as IEEE fp16) */
   int32_t batch, H, W, Cin;   /* conv mode geometry; EPI_CONVT: input grid */
@@ -131,6 +131,8 @@ typedef struct ada_gemm_desc {
   int32_t ldo, P, ks, cout, sigmoid;
   int32_t force_bn;     /* 0 = auto, else 32/64/128/256 */
   int32_t force_cg;     /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
+  int32_t conv_stride;  /* conv mode: 0 / 1 = stride 1; 2 = stride 2 (resize_layers[3], dpt.py:102-107): H, W describe the
+                           INPUT map, the output is ((H-1)/2+1) x ((W-1)/2+1) */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
 /* out[rows or B*(n_tok-1), D] bf16 = LayerNorm((x + delta) + delta2) (block.py:84,87,105-106; dinov2.py:337-340 when
@@ -179,8 +181,6 @@ int ada_op_upsample(const void* in_bf16, void* out_bf16, int32_t B, int32_t Hi, 
 /* fp32 NCHW planes -> bf16 patch matrix [B*P, Kpad] (dav2.py:65,73-74 + patch_embed.py:76 im2col-free gather). */
 int ada_op_patch_gather(const float* rgb, const float* const* guides, const int32_t* guide_ch, int32_t n_guides,
                         void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t Kpad, void* stream);
-/* stride-2 3x3 gather for resize_layers[3] (dpt.py:102-107): NHWC -> [B*Ho*Wo, 9*C]. */
-int ada_op_im2col_s2(const void* in_bf16, void* out_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* Fused tail (dpt.py:194-195): V = per-tap 1x1 contractions of output_conv2.0 applied to the low-res output_conv1 map,
  * NHWC fp16 [B,Hl,Wl,288] (ada_op_gemm with epi = 10); out[b,y,x] = sigmoid(w3 . relu(b2 + sum_taps bilinear_align_corners(V_tap)(y+dy, x+dx)) + b3),
  * aux = [w3 (32), b3]. Requires the 8h -> 14h geometry (Hl*14 == H*8). */

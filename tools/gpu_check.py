@@ -287,17 +287,21 @@ def chk_patch_gather():
     return r
 
 
-def chk_im2col():
+def chk_conv_s2(B, H, W, Cin, Cout):
+    """3x3, stride 2, pad 1 (resize_layers[3], dpt.py:102-107) as an implicit GEMM: the tensor map walks the input with
+    element stride 2; odd and even input sizes, ragged output tiles."""
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(10)
-    B, H, W, C = 2, 37, 37, 64
-    x = torch.randn(B, H, W, C, generator=g, device="cuda").bfloat16()
-    out = ops.im2col_s2(x)
+    x = torch.randn(B, Cin, H, W, generator=g, device="cuda").bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, device="cuda") * (1.0 / (3 * Cin ** 0.5))
+    bias = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    ref = torch.nn.functional.conv2d(x.float(), w.bfloat16().float(), bias, stride=2, padding=1)
+    Ho, Wo = ref.shape[2:]
+    out = torch.zeros(B, Ho, Wo, Cout, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), conv=(B, H, W, Cin), N=Cout, bias=bias, out_bf16=out,
+             ldo=Cout, conv_stride=2)
     torch.cuda.synchronize()
-    ref = torch.nn.functional.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L] (c-major)
-    Ho = (H - 1) // 2 + 1
-    ref = ref.view(B, C, 9, Ho * Ho).permute(0, 3, 2, 1).reshape(B * Ho * Ho, 9 * C)
-    return _cmp("im2col", out, ref, 0, 0)
+    return _cmp("conv_s2", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
 
 
 def chk_gemm_resid_f32(M, N, K, gamma=True, cg=0):
@@ -378,7 +382,9 @@ CHECKS = {
     "fused_tail_5x7": lambda: chk_fused_tail(5, 7),
     "fused_tail_9x9": lambda: chk_fused_tail(9, 9),
     "patch_gather": chk_patch_gather,
-    "im2col_s2": chk_im2col,
+    "conv_s2_37": lambda: chk_conv_s2(2, 37, 37, 128, 192),
+    "conv_s2_74x50": lambda: chk_conv_s2(1, 74, 50, 64, 64),
+    "conv_s2_1024": lambda: chk_conv_s2(2, 37, 37, 1024, 1024),
 }
 
 
