@@ -209,6 +209,8 @@ def timed_loop(torch, fn, steps, warmup, barrier):
 def parity_check(torch, model, x, mask, obs, out, idx=0):
     """One image of the timed output against the CPU oracle on the same weights / inputs (outside every timed region)."""
     from oracle import amodal_oracle as O
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))  # torchrun pins OMP_NUM_THREADS=1
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
     xi, mi, oi = x[idx:idx + 1].cpu(), mask[idx:idx + 1].cpu(), obs[idx:idx + 1].cpu()
     t0 = time.perf_counter()
