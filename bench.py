@@ -46,12 +46,21 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 100 ms while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons every 100 ms. It is started BEFORE the warm-up (NVML start-up takes up to
+    a second and must not land inside the timed region) and only the samples that arrive between mark_begin() and
+    mark_end() -- the timed region -- are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, uuid):
         self.rows, self.proc, self.uuid = [], None, uuid
+        self.t_begin, self.t_end = None, None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -65,7 +74,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -77,7 +86,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t_begin or 0.0
+        t1 = (self.t_end or time.time()) + 0.05
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -332,13 +345,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        out = step()
-    barrier()
     sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(a.warmup):
+        out = step()
+    barrier()
+    time.sleep(0.3)  # (all ranks) let nvidia-smi finish starting up outside the timed region
+    for _ in range(2):
+        out = step()
+    barrier()
+    if sampler:
+        sampler.mark_begin()
     ms, out = timed_loop(torch, step, a.steps, 0, barrier)
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ms, dev)
     launches = model.launch_count()
