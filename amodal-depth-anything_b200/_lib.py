@@ -19,6 +19,7 @@ ADA_OK, ADA_EINVAL, ADA_ENODEVICE, ADA_ECUDA, ADA_ESTATE = 0, -1, -2, -3, -4
 EPI_BF16, _EPI_UNUSED, EPI_EMBED, EPI_CONVT, EPI_TAIL, EPI_SWIGLU = range(6)
 EPI_RESID_F32 = 9  # out_f32 += (acc + bias) * gamma, in place through TMA (csrc/gemm.cuh)
 EPI_F16 = 10       # EPI_BF16 without activation / residuals, stored as fp16 (tap map of the fused tail)
+EPI_BF16_CHLN = 11  # conv + per-pixel channel LayerNorm + ReLU (bias = conv bias, gamma / aux = LN weight / bias), N <= 256
 ACT_NONE, ACT_GELU, ACT_RELU = range(3)
 A_LINEAR, A_CONV3X3 = range(2)
 

@@ -237,6 +237,12 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   int bn = L.force_bn ? L.force_bn : pick_bn(g.epi == EPI_SWIGLU ? std::max(L.N, 64) : L.N);
   if (!L.force_bn && L.a_mode == A_LINEAR && L.K <= 256 && L.N > 64 && bn < 128) bn = 128;  // store-bound: fewer, wider tiles
   if (g.epi == EPI_TAIL) bn = 32;
+  if (g.epi == EPI_BF16_CHLN) {
+    ADA_REQUIRE(L.N <= 256 && L.N % 8 == 0 && g.gamma != nullptr && g.aux != nullptr && g.act == ACT_NONE &&
+                    g.resid1 == nullptr && g.resid2 == nullptr && L.out_relu == nullptr,
+                "EPI_BF16_CHLN: N <= 256, LayerNorm weight (gamma) and bias (aux), no activation / residuals");
+    bn = 256;
+  }
   if (g.epi == EPI_SWIGLU && bn < 128) bn = 128;
   ADA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "bad BN");
   ADA_REQUIRE(bn != 32 || g.epi == EPI_TAIL, "BN=32 is only built for the fused tail epilogue");
@@ -329,7 +335,7 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
 #else
   g.debug_timeline = 0;
 #endif
-  if (g.epi == EPI_BF16 || g.epi == EPI_F16 || g.epi == EPI_SWIGLU) {
+  if (g.epi == EPI_BF16 || g.epi == EPI_F16 || g.epi == EPI_SWIGLU || g.epi == EPI_BF16_CHLN) {
     const int n_out = (g.epi == EPI_SWIGLU) ? L.N / 2 : L.N;
     ADA_REQUIRE(g.out_bf16 != nullptr && g.ldo % 8 == 0 && n_out % 8 == 0, "bf16 output needs ldo, N multiples of 8");
     auto make_c = [&](const void* ptr) {
@@ -410,6 +416,8 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_GEMM_CASE(128, 1, EPI_F16)
   ADA_GEMM_CASE(256, 1, EPI_F16)
   ADA_GEMM_CASE(256, 2, EPI_F16)
+  ADA_GEMM_CASE(256, 1, EPI_BF16_CHLN)
+  ADA_GEMM_CASE(256, 2, EPI_BF16_CHLN)
   ADA_GEMM_CASE(64, 1, EPI_RESID_F32)
   ADA_GEMM_CASE(128, 1, EPI_RESID_F32)
   ADA_GEMM_CASE(256, 1, EPI_RESID_F32)
@@ -1456,9 +1464,31 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
       launch_gemm(L, st);
     }
     if (c.input_projection) {  // input_projection[i]: conv3x3 + channel LN + ReLU (dpt.py:153-159,178-179)
-      conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
-      launch_channel_ln_relu(m->ipb[i], m->ipln_w[i], m->ipln_b[i], m->ipb[i], static_cast<long long>(B) * sh[i] * sw[i],
-                             Ci, 1e-6f, st);
+      static const int chln_epi = env_int("ADA_CHLN_EPI", 1);
+      if (chln_epi && Ci <= 256) {  // all channels of a pixel in one accumulator tile: LayerNorm + ReLU in the conv epilogue
+        GemmLaunch L;
+        L.A = m->rs[i];
+        L.Bw = m->ip[i].w;
+        L.M = B * sh[i] * sw[i];
+        L.N = Ci;
+        L.ldb = m->ip[i].ldw;
+        L.a_mode = A_CONV3X3;
+        L.batch = B;
+        L.H = sh[i];
+        L.W = sw[i];
+        L.Cin = Ci;
+        L.args.epi = EPI_BF16_CHLN;
+        L.args.bias = m->ip[i].b;
+        L.args.gamma = m->ipln_w[i];
+        L.args.aux = m->ipln_b[i];
+        L.args.out_bf16 = m->ipb[i];
+        L.args.ldo = Ci;
+        launch_gemm(L, st);
+      } else {
+        conv3x3(m->rs[i], B, sh[i], sw[i], m->ip[i], ACT_NONE, nullptr, nullptr, m->ipb[i], nullptr, st);
+        launch_channel_ln_relu(m->ipb[i], m->ipln_w[i], m->ipln_b[i], m->ipb[i], static_cast<long long>(B) * sh[i] * sw[i],
+                               Ci, 1e-6f, st);
+      }
     }
     // layer{i}_rn: conv3x3 C_i -> F, no bias (blocks.py:20-24); keep x and relu(x) for the residual units
     conv3x3(m->ipb[i], B, sh[i], sw[i], m->rn[i], ACT_NONE, nullptr, nullptr, m->rnb[i], m->rnr[i], st);

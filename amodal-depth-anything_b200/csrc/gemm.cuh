@@ -69,7 +69,15 @@ enum EpiMode : int {
   // EPI_BF16 without activation / residuals, stored as IEEE fp16 instead of bf16: the per-tap contraction map of the fused
   // tail (output_conv2.0 applied at low resolution), whose consumer interpolates it with packed fp16 FMAs. Values are O(1);
   // fp16 keeps three more mantissa bits than bf16.
-  EPI_F16 = 10
+  EPI_F16 = 10,
+  // conv3x3 + per-pixel LayerNorm over the channels + ReLU in one pass (input_projection of the guided head, dpt.py:153-159:
+  // Conv2d, channels_first LayerNorm of dpt.py:37-61 with eps 1e-6 and biased variance, ReLU). Needs every channel of a
+  // pixel in one accumulator tile: N <= 256, BN = 256. Each epilogue thread owns a whole 256-column row (warpgroup h drains
+  // the tiles of accumulator stage h instead of half the columns of every tile), reads its row from tensor memory three
+  // times (mean, variance, normalise) and stores bf16 through TMA. The statistics are taken from the fp32 accumulators,
+  // not from a bf16-rounded conv output as the separate channel_ln_relu_kernel has to.
+  // bias = conv bias, gamma = LayerNorm weight, aux = LayerNorm bias.
+  EPI_BF16_CHLN = 11
 };
 __host__ __device__ constexpr bool epi_is_bf16(int e) {
   return e == EPI_BF16 || e == EPI_BF16_GELU || e == EPI_BF16_RELU || e == EPI_BF16_RESID || e == EPI_F16;
@@ -200,7 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8 * CG);  // one arrive per epilogue warp of every CTA in the pair
+      mbar_init(tempty_bar(s), (EPI == EPI_BF16_CHLN ? 4 : 8) * CG);  // one arrive per epilogue warp (CHLN: per warp of the warpgroup that owns the stage) of every CTA in the pair
     }
     fence_barrier_init();
   }
@@ -348,7 +356,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #else
     auto stamp = [](int) {};
 #endif
+    if constexpr (EPI == EPI_BF16_CHLN) {  // single N tile: the conv bias is staged once
+      for (int i = et; i < BN; i += kEpiThreads) s_vec[i] = (g.bias != nullptr && i < g.N) ? __ldg(g.bias + i) : 0.0f;
+      named_bar_sync(1, kEpiThreads);
+    }
     for (int t = unit; t < num_tiles; t += num_units) {
+      if constexpr (EPI == EPI_BF16_CHLN) {
+        if (acc != half) {  // the other warpgroup owns this accumulator stage
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
+      }
       const int mt = t / tiles_n, nt = t % tiles_n;
       const int n0 = nt * BN;
       stamp(0);
@@ -432,7 +450,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       stamp(2);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      if constexpr (tma_out) {
+      if constexpr (EPI == EPI_BF16_CHLN) {
+        if constexpr (BN == 256) {
+          const float inv_n = 1.0f / static_cast<float>(g.N);
+          const int ngroups = (g.N + 63) >> 6;
+          // pass 1: mean of (acc + conv bias) over the N channels of this pixel
+          float sum = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < 2 * ngroups; ++c32) {
+            uint32_t r[32];
+            tmem_ld32(t_addr + c32 * 32, r);
+            tmem_ld_wait();
+            const float* bb = s_bias + c32 * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (c32 * 32 + j < g.N) {  // N % 8 == 0
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sum += __uint_as_float(r[j + k]) + bb[j + k];
+              }
+          }
+          const float mean = sum * inv_n;
+          // pass 2: biased variance (two-pass, as dpt.py:56-58)
+          float sq = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < 2 * ngroups; ++c32) {
+            uint32_t r[32];
+            tmem_ld32(t_addr + c32 * 32, r);
+            tmem_ld_wait();
+            const float* bb = s_bias + c32 * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (c32 * 32 + j < g.N) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float d = __uint_as_float(r[j + k]) + bb[j + k] - mean;
+                  sq = fmaf(d, d, sq);
+                }
+              }
+          }
+          const float rstd = 1.0f / sqrtf(sq * inv_n + 1e-6f);
+          // pass 3: normalise, affine, ReLU, bf16, TMA store (columns past N are clipped by the tensor map)
+#pragma unroll 1
+          for (int cg = 0; cg < ngroups; ++cg) {
+            const int oc = cg * 64;
+            uint32_t pk[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld32(t_addr + oc + h * 32, r);
+              tmem_ld_wait();
+              const float* bb = s_bias + oc + h * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int col = oc + h * 32 + j;
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
+                if (col < g.N) {
+                  w4 = __ldg(reinterpret_cast<const float4*>(g.gamma + col));
+                  b4 = __ldg(reinterpret_cast<const float4*>(g.aux + col));
+                }
+                const float y0 = fmaxf(fmaf((__uint_as_float(r[j]) + bb[j] - mean) * rstd, w4.x, b4.x), 0.f);
+                const float y1 = fmaxf(fmaf((__uint_as_float(r[j + 1]) + bb[j + 1] - mean) * rstd, w4.y, b4.y), 0.f);
+                const float y2 = fmaxf(fmaf((__uint_as_float(r[j + 2]) + bb[j + 2] - mean) * rstd, w4.z, b4.z), 0.f);
+                const float y3 = fmaxf(fmaf((__uint_as_float(r[j + 3]) + bb[j + 3] - mean) * rstd, w4.w, b4.w), 0.f);
+                pk[h * 16 + (j >> 1)] = pack_bf16x2(y0, y1);
+                pk[h * 16 + (j >> 1) + 1] = pack_bf16x2(y2, y3);
+              }
+            }
+            const uint32_t buf = buf0 + static_cast<uint32_t>(sbuf) * 4096u;
+            bulk_wait_read_w<Cfg::kStgBufs - 1>();  // (elected lane) the store that last used this buffer has drained it
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              st_shared_v4(buf + st_row + ((static_cast<uint32_t>(c) ^ st_sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
+                           pk[4 * c + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (g.a_mode == A_CONV3X3)
+              tma_store_4d_commit_w(&tmap_c, buf, oc, x0, y0 + 2 * q, img);
+            else
+              tma_store_2d_commit_w(&tmap_c, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
+            if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
+          }
+        }
+      } else if constexpr (tma_out) {
         if constexpr (BN >= 64) {
           constexpr int out_cols = (EPI == EPI_SWIGLU) ? BN / 2 : BN;  // output columns produced by this tile
           const int on0 = (EPI == EPI_SWIGLU) ? (n0 >> 1) : n0;

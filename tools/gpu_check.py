@@ -112,6 +112,17 @@ def chk_conv(B, H, W, Cin, Cout, mode, cg=0):
         a["relu_copy_ok"] = b["ok"]
         a["ok"] = a["ok"] and b["ok"]
         return a
+    if mode == "chln":  # conv + channel LayerNorm + ReLU in the epilogue (dpt.py:153-159)
+        lw = 1.0 + 0.2 * torch.randn(Cout, generator=g, device="cuda")
+        lb = 0.3 * torch.randn(Cout, generator=g, device="cuda")
+        out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), N=Cout, epi=L.EPI_BF16_CHLN, bias=bias, gamma=lw, aux=lb, out_bf16=out,
+                 ldo=Cout, force_cg=cg)
+        torch.cuda.synchronize()
+        u = ref.mean(1, keepdim=True)
+        sv = (ref - u).pow(2).mean(1, keepdim=True)
+        ref2 = torch.relu((ref - u) / torch.sqrt(sv + 1e-6) * lw.view(1, -1, 1, 1) + lb.view(1, -1, 1, 1))
+        return _cmp("conv_chln", out.permute(0, 3, 1, 2), ref2, 3e-2, 1e-2)
     if mode == "tail":
         assert Cout == 32
         w2 = torch.randn(32, generator=g, device="cuda") * 0.3
@@ -382,6 +393,10 @@ CHECKS = {
     "fused_tail_5x7": lambda: chk_fused_tail(5, 7),
     "fused_tail_9x9": lambda: chk_fused_tail(9, 9),
     "patch_gather": chk_patch_gather,
+    "conv_chln_256": lambda: chk_conv(2, 37, 45, 256, 256, "chln"),
+    "conv_chln_256_cg2": lambda: chk_conv(2, 40, 70, 256, 256, "chln", cg=2),
+    "conv_chln_48": lambda: chk_conv(2, 20, 33, 48, 48, "chln"),
+    "conv_chln_192": lambda: chk_conv(1, 37, 37, 192, 192, "chln"),
     "conv_s2_37": lambda: chk_conv_s2(2, 37, 37, 128, 192),
     "conv_s2_74x50": lambda: chk_conv_s2(1, 74, 50, 64, 64),
     "conv_s2_1024": lambda: chk_conv_s2(2, 37, 37, 1024, 1024),
