@@ -102,7 +102,7 @@ SIGNATURES = {
     "ada_interp_pos_embed_host": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "ada_op_gemm": (c_int32, [POINTER(GemmDesc), c_void_p]),
     "ada_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
-                                   c_int32, c_int32, c_int32, c_void_p]),
+                                   c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ada_pre_image_nearest": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "ada_pre_mask_nearest": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "ada_post_minmax_normalize": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

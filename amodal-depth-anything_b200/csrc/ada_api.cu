@@ -444,18 +444,27 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------ other launchers
 static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bfloat16* delta2, const float* w, const float* b,
                              __nv_bfloat16* out, int rows, int D, float eps, int n_tok, int drop_cls, int write_x,
-                             cudaStream_t st) {
+                             cudaStream_t st, const float* w2 = nullptr, const float* b2 = nullptr,
+                             __nv_bfloat16* out2 = nullptr) {
   const int grid = (rows + 7) / 8;
   ADA_REQUIRE(delta != nullptr || delta2 == nullptr, "layernorm: delta2 without delta");
+  ADA_REQUIRE(out2 == nullptr || (w2 != nullptr && b2 != nullptr && !drop_cls && n_tok > 1), "layernorm: second output needs w2 / b2, a full first output and n_tok");
   ProfScope prof(PC_LAYERNORM, 0.0,
-                 (6.0 + (delta ? 2.0 : 0.0) + (delta2 ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0)) * rows * static_cast<double>(D), st);
+                 (6.0 + (delta ? 2.0 : 0.0) + (delta2 ? 2.0 : 0.0) + (delta && write_x ? 4.0 : 0.0) + (out2 ? 2.0 : 0.0)) * rows *
+                     static_cast<double>(D), st);
+#define ADA_LN_CASE(C)                                                                                                      \
+  case C:                                                                                                                   \
+    launch_pdl(layernorm_rows_kernel<C>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, \
+               write_x, w2, b2, out2);                                                                                     \
+    break;
   switch (D / 128) {
-    case 3: launch_pdl(layernorm_rows_kernel<3>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 6: launch_pdl(layernorm_rows_kernel<6>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 8: launch_pdl(layernorm_rows_kernel<8>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
-    case 12: launch_pdl(layernorm_rows_kernel<12>, dim3(grid), dim3(256), 0, st, x, delta, delta2, w, b, out, rows, eps, n_tok, drop_cls, write_x); break;
+    ADA_LN_CASE(3)
+    ADA_LN_CASE(6)
+    ADA_LN_CASE(8)
+    ADA_LN_CASE(12)
     default: throw AdaError(ADA_EINVAL, "layernorm: embed_dim must be 384/768/1024/1536");
   }
+#undef ADA_LN_CASE
   ADA_REQUIRE(D % 128 == 0, "layernorm: D % 128");
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
@@ -1349,10 +1358,16 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   //      the stream's HBM traffic): 658 vs 665 img/s, so it stays off.
   static const int resid_epi = env_int("ADA_RESID_EPI", 0);
   int tap_i = 0;
+  int pending_tap = -1;  // tap whose LayerNorm rides on the next block's norm1
   const __nv_bfloat16 *pend1 = nullptr, *pend2 = nullptr;  // residual-branch outputs not yet added to x
   for (int i = 0; i < c.depth; ++i) {
     const BlockW& w = m->blocks[i];
-    launch_layernorm(m->x, pend1, pend2, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, pend1 != nullptr, st);
+    // norm1; if the previous block was tapped, the same pass also emits its tap (shared final norm, cls dropped, NHWC):
+    // identical input, identical statistics, only the affine differs (dinov2.py:337-340)
+    launch_layernorm(m->x, pend1, pend2, w.ln1w, w.ln1b, m->xn, M, D, 1e-6f, N, 0, pend1 != nullptr, st,
+                     pending_tap >= 0 ? m->normw : nullptr, pending_tap >= 0 ? m->normb : nullptr,
+                     pending_tap >= 0 ? m->tap[pending_tap] : nullptr);
+    pending_tap = -1;
     {
       GemmArgs e{};
       e.epi = EPI_BF16;
@@ -1411,9 +1426,13 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
       pend2 = m->ybuf2;
     }
     if (tap_i < 4 && i == c.taps[tap_i]) {
-      // shared final norm of x (+ both pending branches), cls dropped, NHWC patch map (dinov2.py:337-340); x itself is
-      // updated by the next block's first LayerNorm, so nothing is written back here
-      launch_layernorm(m->x, pend1, pend2, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
+      // shared final norm of x (+ both pending branches), cls dropped, NHWC patch map (dinov2.py:337-340). Fused into the
+      // next block's norm1 when there is one (and the residual epilogue variant is off: then x is already complete);
+      // after the last block it is a pass of its own, and x is not written back.
+      if (i + 1 < c.depth && !resid_epi)
+        pending_tap = tap_i;
+      else
+        launch_layernorm(m->x, pend1, pend2, m->normw, m->normb, m->tap[tap_i], M, D, 1e-6f, N, 1, 0, st);
       ++tap_i;
     }
   }
@@ -1917,12 +1936,12 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
 
 int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, const float* w, const float* b,
                      void* out_bf16, int32_t rows, int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x,
-                     void* stream) {
+                     const float* w2, const float* b2, void* out2_bf16, void* stream) {
   return guarded([&] {
     require_device();
     launch_layernorm(x, static_cast<const __nv_bfloat16*>(delta_bf16), static_cast<const __nv_bfloat16*>(delta2_bf16), w, b,
                      static_cast<__nv_bfloat16*>(out_bf16), rows, D, eps, n_tok, drop_cls, write_x,
-                     static_cast<cudaStream_t>(stream));
+                     static_cast<cudaStream_t>(stream), w2, b2, static_cast<__nv_bfloat16*>(out2_bf16));
   });
 }
 

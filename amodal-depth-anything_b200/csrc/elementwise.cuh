@@ -21,11 +21,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // therefore only ever touched by this coalesced kernel, never by the (row-per-thread) GEMM epilogue. The encoder writes
 // x once per block: norm2 normalises x + attn-branch without storing it, the next norm1 adds both branches and stores
 // (22 instead of 24 bytes per element and block).
+// out2 != nullptr: a second affine of the SAME normalised row, written as the cls-less patch map -- the shared final norm of
+// a tapped block (dinov2.py:337-340) has the same input, hence the same mean / variance, as the next block's norm1, so the
+// tap costs one extra bf16 store instead of another pass over the fp32 stream and both pending branches.
 template <int CHUNKS>  // D = CHUNKS * 128
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
                       const __nv_bfloat16* __restrict__ delta2, const float* __restrict__ w, const float* __restrict__ b,
-                      __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls, int write_x) {
+                      __nv_bfloat16* __restrict__ out, int rows, float eps, int n_tok, int drop_cls, int write_x,
+                      const float* __restrict__ w2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ out2) {
   constexpr int D = CHUNKS * 128;
   griddep_wait();
   griddep_launch_dependents();
@@ -83,6 +87,21 @@ layernorm_rows_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ d
     const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
     const float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
     o[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+  if (out2 != nullptr) {
+    const int bi = row / n_tok, t = row % n_tok;
+    if (t == 0) return;
+    uint2* o2 = reinterpret_cast<uint2*>(out2 + (static_cast<long long>(bi) * (n_tok - 1) + (t - 1)) * D);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w2) + lane + 32 * i);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b2) + lane + 32 * i);
+      const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x;
+      const float y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+      const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
+      const float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+      o2[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
   }
 }
 

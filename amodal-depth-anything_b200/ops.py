@@ -55,15 +55,19 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
     _call(A, lib.ada_op_gemm, ctypes.byref(d))
 
 
-def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=False, delta2=None):
+def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=False, delta2=None, tap_w=None, tap_b=None):
+    """tap_w / tap_b: also return a second affine of the same normalised rows as the cls-less patch map (needs n_tok)."""
     rows, D = x.shape
     if drop_cls:
         out = torch.empty((rows // n_tok) * (n_tok - 1), D, dtype=torch.bfloat16, device=x.device)
     else:
         out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    out2 = None
+    if tap_w is not None:
+        out2 = torch.empty((rows // n_tok) * (n_tok - 1), D, dtype=torch.bfloat16, device=x.device)
     _call(x, L.load().ada_op_layernorm, _p(x), _p(delta), _p(delta2), _p(w), _p(b), _p(out), rows, D, eps, n_tok, int(drop_cls),
-                                      int(write_x))
-    return out
+          int(write_x), _p(tap_w), _p(tap_b), _p(out2))
+    return out if out2 is None else (out, out2)
 
 
 def attention(qkv, B, N, heads, impl=-1):

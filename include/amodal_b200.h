@@ -137,10 +137,12 @@ typedef struct ada_gemm_desc {
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
 /* out[rows or B*(n_tok-1), D] bf16 = LayerNorm((x + delta) + delta2) (block.py:84,87,105-106; dinov2.py:337-340 when
  * drop_cls). x fp32 [rows, D]; delta / delta2 (optional, bf16 [rows, D]) are the pending residual-branch outputs (delta2
- * requires delta); write_x stores the sum back into x. */
+ * requires delta); write_x stores the sum back into x. out2 (optional, with w2 / b2; needs drop_cls == 0): a second affine
+ * of the same normalised rows written as the cls-less patch map [B*(n_tok-1), D] -- the tap of a block riding on the next
+ * block's norm1 (same input, same statistics; dinov2.py:337-340). */
 int ada_op_layernorm(float* x, const void* delta_bf16, const void* delta2_bf16, const float* w, const float* b,
                      void* out_bf16, int32_t rows, int32_t D, float eps, int32_t n_tok, int32_t drop_cls, int32_t write_x,
-                     void* stream);
+                     const float* w2, const float* b2, void* out2_bf16, void* stream);
 /* ---- single-image pre/post-processing of the reference's infer.py on the device. All
  * pointers are device pointers; one image; asynchronous on `stream`. Nearest sampling follows ATen
  * (src = min(floor(dst * in/out), in-1)), which is what torchvision Resize(NEAREST) and F.interpolate's default use. */

@@ -32,7 +32,7 @@ def test_no_cpu_fallback_in_c_abi():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = L.load()
-    rc = lib.ada_op_layernorm(None, None, None, None, None, None, 1, 384, 1e-6, 1, 0, 0, None)
+    rc = lib.ada_op_layernorm(None, None, None, None, None, None, 1, 384, 1e-6, 1, 0, 0, None, None, None, None)
     assert rc == L.ADA_ENODEVICE
     assert b"CUDA" in lib.ada_last_error() or b"device" in lib.ada_last_error()
 

@@ -231,6 +231,34 @@ def chk_layernorm_delta():
     return r
 
 
+def chk_layernorm_tap():
+    """norm1 of the next block and the tap of the previous one in one pass: same statistics, two affines, the second written
+    without the cls rows (dinov2.py:337-340)."""
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(26)
+    B, n_tok, D = 3, 50, 1024
+    x = torch.randn(B * n_tok, D, generator=g, device="cuda") * 2 + 0.3
+    d1 = torch.randn(B * n_tok, D, generator=g, device="cuda").bfloat16()
+    d2 = torch.randn(B * n_tok, D, generator=g, device="cuda").bfloat16()
+    w, b, w2, b2 = (torch.randn(D, generator=g, device="cuda") for _ in range(4))
+    x1 = x.clone()
+    out, tap = ops.layernorm(x1, w, b, 1e-6, n_tok, False, delta=d1, write_x=True, delta2=d2, tap_w=w2, tap_b=b2)
+    torch.cuda.synchronize()
+    xs = (x + d1.float()) + d2.float()
+    r = _cmp("ln", out, torch.nn.functional.layer_norm(xs, (D,), w, b, 1e-6), 2e-2, 1e-2)
+    ref2 = torch.nn.functional.layer_norm(xs, (D,), w2, b2, 1e-6).view(B, n_tok, D)[:, 1:].reshape(-1, D)
+    r2 = _cmp("tap", tap, ref2, 2e-2, 1e-2)
+    # the separate tap pass (what the last block still uses) must give the same bits
+    x2 = x.clone()
+    tap_alone = ops.layernorm(x2, w2, b2, 1e-6, n_tok, True, delta=d1, write_x=False, delta2=d2)
+    torch.cuda.synchronize()
+    r["tap_ok"] = r2["ok"]
+    r["tap_same_bits_as_separate_pass"] = bool(torch.equal(tap, tap_alone))
+    r["x_written"] = bool(torch.equal(x1, xs))
+    r["ok"] = r["ok"] and r2["ok"] and r["tap_same_bits_as_separate_pass"] and r["x_written"]
+    return r
+
+
 def chk_channel_ln(C):
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -381,6 +409,7 @@ CHECKS = {
     "layernorm_1024_drop": lambda: chk_layernorm(1024, True),
     "layernorm_1536": lambda: chk_layernorm(1536, False),
     "layernorm_delta": chk_layernorm_delta,
+    "layernorm_tap_fused": chk_layernorm_tap,
     "channel_ln_48": lambda: chk_channel_ln(48),
     "channel_ln_1024": lambda: chk_channel_ln(1024),
     "upsample_19_37": lambda: chk_upsample(19, 37),
