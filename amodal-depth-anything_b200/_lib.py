@@ -76,6 +76,7 @@ class GemmDesc(ctypes.Structure):
         ("force_bn", c_int32),
         ("force_cg", c_int32),
         ("conv_stride", c_int32),
+        ("conv_taps", c_int32),
     ]
 
 

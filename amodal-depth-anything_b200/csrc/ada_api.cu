@@ -190,6 +190,7 @@ struct GemmLaunch {
   int a_mode = A_LINEAR;
   int batch = 0, H = 0, W = 0, Cin = 0;  // conv: OUTPUT map size
   int conv_stride = 1, Hin = 0, Win = 0;  // conv: stride 1 or 2 and the input map size (0 = same as output)
+  int conv_taps = 9;         // conv: 9 = 3x3, 1 = pointwise on pixel tiles (the k == s transposed convs, EPI_CONVT)
   GemmArgs args{};           // epilogue fields filled by caller
   __nv_bfloat16* out_relu = nullptr;  // EPI_BF16: optional relu(out) copy (second TMA store map)
   int force_bn = 0;
@@ -301,12 +302,14 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     g.tiles_x = (L.W + kTileW * cg - 1) / (kTileW * cg);
     g.tiles_y = (L.H + kTileH - 1) / kTileH;
     g.c_chunks = round_up(L.Cin, kBlockK) / kBlockK;
-    g.K = 9 * g.c_chunks * kBlockK;
+    g.K = L.conv_taps * g.c_chunks * kBlockK;
     const int sd = L.conv_stride;
     ADA_REQUIRE(sd == 1 || sd == 2, "conv stride is 1 or 2");
     const int Hin = L.Hin ? L.Hin : L.H, Win = L.Win ? L.Win : L.W;
     ADA_REQUIRE((Hin - 1) / sd + 1 == L.H && (Win - 1) / sd + 1 == L.W, "conv input / output size mismatch (k3, pad 1)");
     g.conv_stride = sd;
+    g.conv_taps = L.conv_taps;
+    ADA_REQUIRE(L.conv_taps == 9 || (L.conv_taps == 1 && sd == 1 && L.Cin % kBlockK == 0), "pointwise pixel-tile mode: stride 1, Cin % 64 == 0");
     uint64_t dims[4] = {static_cast<uint64_t>(L.Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                         static_cast<uint64_t>(L.batch)};
     uint64_t str[3] = {static_cast<uint64_t>(L.Cin) * 2, static_cast<uint64_t>(Win) * L.Cin * 2,
@@ -356,14 +359,25 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
       g.has_relu_copy = 1;
     }
   }
+  if (g.epi == EPI_CONVT && L.a_mode == A_CONV3X3) {
+    // pixel-shuffle output [B, H*ks, W*ks, Cout] viewed as (kx*Cout + co, x, ky, y, b) for the TMA-store epilogue
+    ADA_REQUIRE(g.out_bf16 != nullptr && g.ks >= 1 && g.cout % 64 == 0 && bn >= 64 && L.N == g.ks * g.ks * g.cout,
+                "EPI_CONVT on pixel tiles: Cout % 64 == 0, N = ks * ks * Cout");
+    const uint64_t co = static_cast<uint64_t>(g.cout), ks = static_cast<uint64_t>(g.ks), Wd = static_cast<uint64_t>(L.W),
+                   Hd = static_cast<uint64_t>(L.H);
+    uint64_t dims[5] = {ks * co, Wd, ks, Hd, static_cast<uint64_t>(L.batch)};
+    uint64_t str[4] = {ks * co * 2, Wd * ks * co * 2, ks * Wd * ks * co * 2, Hd * ks * Wd * ks * co * 2};
+    uint32_t box[5] = {64, static_cast<uint32_t>(kTileW), 1, 2, 1};
+    tc = make_tmap_bf16(g.out_bf16, 5, dims, str, box);
+  }
   if (g.epi == EPI_RESID_F32) {
     ADA_REQUIRE(L.a_mode == A_LINEAR && g.out_f32 != nullptr && g.ldo % 4 == 0, "RESID_F32: linear A, fp32 in/out, ldo % 4");
     tc = make_tmap_f32_2d(g.out_f32, static_cast<uint64_t>(L.N), static_cast<uint64_t>(L.M), static_cast<uint64_t>(g.ldo), 32, 32);
   }
   const int tiles_n = (L.N + bn - 1) / bn;
   const int num_tiles = tiles_m * tiles_n;
-  const double kreal = (L.a_mode == A_CONV3X3) ? 9.0 * L.Cin : static_cast<double>(L.K);
-  ProfScope prof(L.a_mode == A_CONV3X3 ? PC_GEMM_CONV : PC_GEMM_LINEAR, 2.0 * L.M * static_cast<double>(L.N) * kreal,
+  const double kreal = (L.a_mode == A_CONV3X3) ? static_cast<double>(L.conv_taps) * L.Cin : static_cast<double>(L.K);
+  ProfScope prof((L.a_mode == A_CONV3X3 && L.conv_taps == 9) ? PC_GEMM_CONV : PC_GEMM_LINEAR, 2.0 * L.M * static_cast<double>(L.N) * kreal,
                  2.0 * (static_cast<double>(L.M) * kreal + static_cast<double>(L.N) * kreal + static_cast<double>(L.M) * L.N), st);
   if (prof.r) {
     prof.r->m = L.M;
@@ -1460,7 +1474,24 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
       e.W = gw;
       e.ks = ks;
       e.cout = Ci;
-      linear(m->proj[i], BP, Ci, Ci, m->w_rs[i], ks * ks * Ci, Ci, e, st);
+      if (Ci % 64 == 0) {  // pixel-tile A operand: the pixel shuffle goes out through TMA boxes
+        GemmLaunch L;
+        L.A = m->proj[i];
+        L.Bw = m->w_rs[i];
+        L.M = BP;
+        L.N = ks * ks * Ci;
+        L.ldb = Ci;
+        L.a_mode = A_CONV3X3;
+        L.conv_taps = 1;
+        L.batch = B;
+        L.H = gh;
+        L.W = gw;
+        L.Cin = Ci;
+        L.args = e;
+        launch_gemm(L, st);
+      } else {
+        linear(m->proj[i], BP, Ci, Ci, m->w_rs[i], ks * ks * Ci, Ci, e, st);
+      }
     } else if (i == 3) {  // conv 3x3 stride 2 (dpt.py:102-107): implicit GEMM, the tensor map walks the input with stride 2
       GemmLaunch L;
       L.A = m->proj[3];
@@ -1902,6 +1933,7 @@ int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
     L.Cin = d->Cin;
     L.force_bn = d->force_bn;
     L.force_cg = d->force_cg;
+    if (d->a_mode == A_CONV3X3 && d->conv_taps == 1) L.conv_taps = 1;  // pointwise on pixel tiles (EPI_CONVT through TMA boxes)
     if (d->a_mode == A_CONV3X3 && d->conv_stride == 2) {  // H, W of the descriptor are the INPUT map
       L.conv_stride = 2;
       L.Hin = d->H;

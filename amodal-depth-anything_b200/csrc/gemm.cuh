@@ -91,6 +91,7 @@ struct GemmArgs {
   int epi, act;
   // conv geometry (A_CONV3X3) -- also used by EPI_CONVT for the input grid
   int H, W, tiles_x, tiles_y, c_chunks;  // OUTPUT map size; c_chunks = c_pad / 64
+  int conv_taps;        // A_CONV3X3 (pixel-tile A operand): 9 = 3x3 conv, 1 = pointwise (k == s transposed conv, EPI_CONVT)
   int conv_stride;      // A_CONV3X3: 1, or 2 (resize_layers[3], dpt.py:102-107): input pixel = stride * output pixel + tap - 1
   // epilogue operands
   const float* bias;        // [N] (EPI_CONVT: [Cout]) or nullptr
@@ -235,7 +236,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                               : (g.M + kBlockM * CG - 1) / (kBlockM * CG);
   const int num_tiles = tiles_m * tiles_n;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
-  const int num_kb = (g.a_mode == A_CONV3X3) ? 9 * g.c_chunks : (g.K + kBlockK - 1) / kBlockK;
+  const int num_kb = (g.a_mode == A_CONV3X3) ? g.conv_taps * g.c_chunks : (g.K + kBlockK - 1) / kBlockK;
+  const int tap_off = (g.conv_taps == 9) ? 1 : 0;  // 3x3: taps start one pixel up / left (the padding); pointwise: none
 
   // Register rebalancing: the kernel is compiled for 168 regs/thread (384 threads); the producer/MMA warpgroup gives
   // registers back and the two epilogue warpgroups take them (setmaxnreg must dominate each role's code for ptxas).
@@ -271,14 +273,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
           mbar_expect_tx_cluster_w(fb, Cfg::kStageBytes);
           if (g.a_mode == A_CONV3X3)
-            tma_load_4d_cg2_w(sa, &tmap_a, fb, cc * kBlockK, x0 * g.conv_stride + kx - 1, y0 * g.conv_stride + ky - 1, img);
+            tma_load_4d_cg2_w(sa, &tmap_a, fb, cc * kBlockK, x0 * g.conv_stride + kx - tap_off, y0 * g.conv_stride + ky - tap_off, img);
           else
             tma_load_2d_cg2_w(sa, &tmap_a, fb, kb * kBlockK, m_row0);
           tma_load_2d_cg2_w(sb, &tmap_b, fb, kb * kBlockK, n_row0);
         } else {
           mbar_expect_tx_w(full_bar(stage), Cfg::kStageBytes);
           if (g.a_mode == A_CONV3X3)
-            tma_load_4d_w(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 * g.conv_stride + kx - 1, y0 * g.conv_stride + ky - 1, img);
+            tma_load_4d_w(sa, &tmap_a, full_bar(stage), cc * kBlockK, x0 * g.conv_stride + kx - tap_off, y0 * g.conv_stride + ky - tap_off, img);
           else
             tma_load_2d_w(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_row0);
           tma_load_2d_w(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_row0);
@@ -706,6 +708,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (valid) g.out_f32[orow] = s;
         }
       } else {
+        // EPI_CONVT on pixel tiles (A operand fetched as 8x16 pixel patches, Cout % 64 == 0): the pixel shuffle of a k == s
+        // transposed conv is a 5-D tensor (kx*Cout + co, x, ky, y, b); a 64-column group of the GEMM output is one (ky, kx) and
+        // 64 consecutive channels, and the 32 rows of a warp are two 16-pixel rows of the patch -- one TMA box, the parts past
+        // the image clipped. (TMA stores take no negative coordinates -- illegal instruction, tools/micro/tma5d_test.cu -- so a
+        // linear M tiling, whose warps wrap around image rows, cannot be expressed as boxes.) The per-thread scatter this
+        // replaces wrote 16 bytes per lane to 32 different cache lines (262 - 485 TFLOP/s on the two resize layers).
+        bool convt_tma = false;
+        if constexpr (EPI == EPI_CONVT && BN >= 64) convt_tma = (g.a_mode == A_CONV3X3) && (g.cout % 64) == 0;
+        if (convt_tma) {
+          if constexpr (EPI == EPI_CONVT && BN >= 64) {
+#pragma unroll 1
+            for (int cg = half; cg < BN / 64; cg += 2) {
+              const int oc = n0 + cg * 64;
+              if (oc >= g.N) break;
+              const int kk = oc / g.cout, co0 = oc - kk * g.cout;
+              const int ky = kk / g.ks, kx = kk - ky * g.ks;
+              uint32_t pk[32];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(t_addr + cg * 64 + h * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + co0 + h * 32 + j));
+                  pk[h * 16 + (j >> 1)] = pack_bf16x2(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y);
+                  pk[h * 16 + (j >> 1) + 1] = pack_bf16x2(__uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
+                }
+              }
+              const uint32_t buf = buf0 + static_cast<uint32_t>(sbuf) * 4096u;
+              bulk_wait_read_w<Cfg::kStgBufs - 1>();
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                st_shared_v4(buf + st_row + ((static_cast<uint32_t>(c) ^ st_sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
+                             pk[4 * c + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              tma_store_5d_w(&tmap_c, buf, kx * g.cout + co0, x0, ky, y0 + 2 * q, img);
+              bulk_commit_w();
+              if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
+            }
+          }
+        } else {
         // EPI_EMBED / EPI_CONVT: direct per-thread stores (one GEMM each per forward; row remap / pixel-shuffle scatter)
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
@@ -755,6 +802,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
           }
+        }
         }
       }
       // accumulator stage drained -> hand it back to the MMA warp

@@ -28,7 +28,7 @@ def _call(t, fn, *args):
 
 def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_f32=None, out_f32=None, out_bf16=None,
          out_relu=None, resid1=None, resid2=None, aux=None, ldo=0, P=0, ks=0, cout=0, sigmoid=0, force_bn=0,
-         force_cg=0, conv=None, N=None, K=None, M=None, H=0, W=0, conv_stride=1):
+         force_cg=0, conv=None, N=None, K=None, M=None, H=0, W=0, conv_stride=1, conv_taps=9):
     """A: bf16 [M,K] (linear) or NHWC bf16 [B,H,W,Cin] (conv=(B,H,W,Cin)); Wt: bf16 [N,Kw]."""
     lib = L.load()
     d = L.GemmDesc()
@@ -52,6 +52,7 @@ def gemm(A, Wt, *, epi=L.EPI_BF16, act=L.ACT_NONE, bias=None, gamma=None, resid_
     d.ldo, d.P, d.ks, d.cout, d.sigmoid, d.force_bn = ldo, P, ks, cout, sigmoid, force_bn
     d.force_cg = force_cg
     d.conv_stride = conv_stride
+    d.conv_taps = conv_taps
     _call(A, lib.ada_op_gemm, ctypes.byref(d))
 
 

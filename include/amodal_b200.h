@@ -133,6 +133,8 @@ typedef struct ada_gemm_desc {
   int32_t force_cg;     /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
   int32_t conv_stride;  /* conv mode: 0 / 1 = stride 1; 2 = stride 2 (resize_layers[3], dpt.py:102-107): H, W describe the
                            INPUT map, the output is ((H-1)/2+1) x ((W-1)/2+1) */
+  int32_t conv_taps;    /* conv mode: 0 / 9 = 3x3 taps; 1 = pointwise on 8x16 pixel tiles (Cin % 64 == 0) -- the k == s transposed
+                           convs (epi 3) then store their pixel shuffle through TMA boxes (Cout % 64 == 0) */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);
 /* out[rows or B*(n_tok-1), D] bf16 = LayerNorm((x + delta) + delta2) (block.py:84,87,105-106; dinov2.py:337-340 when

@@ -135,18 +135,22 @@ def chk_conv(B, H, W, Cin, Cout, mode, cg=0):
         return _cmp("tail", out, torch.sigmoid(z), 5e-3, 0)
 
 
-def chk_convT(ks):
+def chk_convT(ks, Cin=96, Cout=96, B=2, H=37, W=37, pix=False):
+    """pix: A operand on 8x16 pixel tiles, pixel shuffle stored through 5-D TMA boxes (Cin, Cout % 64 == 0)."""
     torch, L, ops = _imports()
-    B, H, W, Cin, Cout = 2, 37, 37, 96, 96
     g = torch.Generator(device="cuda").manual_seed(4)
     x = torch.randn(B, Cin, H, W, generator=g, device="cuda").bfloat16()
     w = torch.randn(Cin, Cout, ks, ks, generator=g, device="cuda") * 0.1
     bias = torch.randn(Cout, generator=g, device="cuda") * 0.1
     ref = torch.nn.functional.conv_transpose2d(x.float(), w.bfloat16().float(), bias, stride=ks)
-    xa = x.permute(0, 2, 3, 1).reshape(B * H * W, Cin).contiguous()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     wp = ops.pack_convT(w, ks)
     out = torch.zeros(B, H * ks, W * ks, Cout, dtype=torch.bfloat16, device="cuda")
-    ops.gemm(xa, wp, epi=L.EPI_CONVT, bias=bias, out_bf16=out, ks=ks, cout=Cout, H=H, W=W)
+    if pix:
+        ops.gemm(x_nhwc, wp, conv=(B, H, W, Cin), conv_taps=1, N=ks * ks * Cout, epi=L.EPI_CONVT, bias=bias, out_bf16=out, ks=ks,
+                 cout=Cout)
+    else:
+        ops.gemm(x_nhwc.reshape(B * H * W, Cin), wp, epi=L.EPI_CONVT, bias=bias, out_bf16=out, ks=ks, cout=Cout, H=H, W=W)
     torch.cuda.synchronize()
     return _cmp("convT", out.permute(0, 3, 1, 2), ref, 3e-2, 1e-2)
 
@@ -390,6 +394,12 @@ CHECKS = {
     "conv_tail": lambda: chk_conv(1, 70, 84, 64, 32, "tail"),
     "convT_k4": lambda: chk_convT(4),
     "convT_k2": lambda: chk_convT(2),
+    # Cout % 64 == 0: pixel shuffle through the 5-D TMA store (warps whose 32 pixels span 1, 2 and up to 7 image rows)
+    "convT_k4_c256_tma": lambda: chk_convT(4, 256, 256, pix=True),
+    "convT_k2_c512_tma": lambda: chk_convT(2, 128, 512, pix=True),
+    "convT_k4_c64_w5_tma": lambda: chk_convT(4, 64, 64, B=3, H=7, W=5, pix=True),
+    "convT_k2_c128_w49_tma": lambda: chk_convT(2, 192, 128, B=1, H=37, W=49, pix=True),
+    "convT_k2_c256_linear": lambda: chk_convT(2, 256, 256),
     # both attention kernels on every shape (impl 0 = attention.cuh, 1 = attention2.cuh), then the auto-selected one
     **{f"attention{i}_small": (lambda i=i: chk_attention(1, 128, 1, impl=i)) for i in (0, 1)},
     **{f"attention{i}_ragged": (lambda i=i: chk_attention(1, 200, 2, impl=i)) for i in (0, 1)},
