@@ -484,12 +484,13 @@ static void launch_layernorm(float* x, const __nv_bfloat16* delta, const __nv_bf
   ++g_launches;
 }
 
-template <int EMU, bool STAGGER, int WAITP>
+template <int EMU, bool STAGGER, int WAITP, bool SPLIT = false>
 static void launch_attention_fa(const CUtensorMap& tm, const CUtensorMap& tmo, const FaArgs& fa, cudaStream_t st) {
   static std::atomic<uint64_t> attr_done{0};
-  ensure_smem_attr(attention_fa_kernel<EMU, STAGGER, WAITP>, kFaSmemBytes, attr_done);
+  ensure_smem_attr(attention_fa_kernel<EMU, STAGGER, WAITP, SPLIT>, kFaSmemBytes, attr_done);
   const int grid = std::min(fa.total_units, device_info().sms);  // persistent: one CTA per SM
-  launch_pdl(attention_fa_kernel<EMU, STAGGER, WAITP>, dim3(grid), dim3(kFaThreads), kFaSmemBytes, st, tm, tmo, fa);
+  launch_pdl(attention_fa_kernel<EMU, STAGGER, WAITP, SPLIT>, dim3(grid), dim3(SPLIT ? kFaThreadsSplit : kFaThreads),
+             kFaSmemBytes, st, tm, tmo, fa);
 }
 
 static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t st,
@@ -528,6 +529,12 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
   fa.total_units = B * heads * fa.units_per_seq;
   fa.scale_log2e = a.scale_log2e;
   const int impl_sel = force_impl >= 0 ? force_impl : impl_env;
+  if (impl_sel == 2) {  // attention2.cuh, two threads per score row (the arithmetic of attention.cuh in the persistent frame)
+    launch_attention_fa<6, false, 2, true>(tm, tmo, fa, st);
+    ADA_CHECK_CUDA(cudaGetLastError());
+    ++g_launches;
+    return;
+  }
   const bool use_fa = impl_sel == 1;
   if (use_fa) {
 #ifdef ADA_BRINGUP
@@ -552,7 +559,9 @@ static void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B
       ADA_FA_CASE(0)
       ADA_FA_CASE(4)
       ADA_FA_CASE(6)
-      default: throw AdaError(ADA_EINVAL, "ADA_ATT_EMU must be one of 0, 4, 6");
+      ADA_FA_CASE(-1)
+      ADA_FA_CASE(-2)
+      default: throw AdaError(ADA_EINVAL, "ADA_ATT_EMU must be one of 0, 4, 6 (-1 / -2: timing skeletons)");
     }
 #undef ADA_FA_CASE
 #else
@@ -1804,17 +1813,10 @@ int ada_forward(ada_handle h, const float* rgb, const float* const* guides, cons
 size_t ada_workspace_bytes(ada_handle h) { return h ? h->arena.bytes : 0; }
 
 int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W) {
+  // counted while launching: exact for the shape of the last forward, 0 before the first one
   if (!h) return -1;
-  (void)B; (void)H; (void)W;
-  if (h->last_launches > 0) return h->last_launches;
-  const ada_config& c = h->cfg;
-  // gather + cls + embed | per block: 2 LN + 4 GEMM + attention | 4 tap LN | head
-  int n = 3 + c.depth * 7 + 4;
-  n += 4 /*projects*/ + 2 /*convT*/ + 1 /*stride-2 conv*/ + 4 * (c.input_projection ? 3 : 1) /*ip conv, LN, rn*/;
-  n += 3 * 6 + 4 /*refinenets: (2+2+1+1) x3, (2+1+1) for #4*/;
-  n += 3 /*oc1, upsample, tail*/;
-  if (h->capture) n += 0;
-  return n;
+  if (h->last_launches > 0 && (B <= 0 || (B == h->last_B && H == h->last_H && W == h->last_W))) return h->last_launches;
+  return 0;
 }
 
 int ada_set_graph(ada_handle h, int32_t on) {
@@ -2045,7 +2047,7 @@ int ada_eval_sample(const float* pred, int32_t h, int32_t w, const float* depth_
 int ada_op_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t heads, int32_t impl, void* stream) {
   return guarded([&] {
     require_device();
-    ADA_REQUIRE(qkv_bf16 && out_bf16 && B > 0 && N > 0 && heads > 0 && impl >= -1 && impl <= 1, "bad argument");
+    ADA_REQUIRE(qkv_bf16 && out_bf16 && B > 0 && N > 0 && heads > 0 && impl >= -1 && impl <= 2, "bad argument");
     launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, N, heads,
                      static_cast<cudaStream_t>(stream), impl);
   });

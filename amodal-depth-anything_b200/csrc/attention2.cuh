@@ -31,14 +31,16 @@
 
 namespace ada {
 
-constexpr int kFaThreads = 384;
+constexpr int kFaThreads = 384;        // one thread per score row
+constexpr int kFaThreadsSplit = 640;   // SPLIT: two threads per score row (16 softmax warps)
 constexpr int kFaStages = 3;                       // K ring and V ring depth
 constexpr int kFaTile = 128 * 64 * 2;              // one 128 x 64 bf16 tile: 16 KB
 constexpr int kFaOffK = 2 * kFaTile;               // after Q0, Q1
 constexpr int kFaOffV = kFaOffK + kFaStages * kFaTile;
 constexpr int kFaOffO = kFaOffV + kFaStages * kFaTile;   // two output staging tiles
 constexpr int kFaOffBar = kFaOffO + 2 * kFaTile;
-constexpr int kFaSmemBytes = kFaOffBar + 256;
+constexpr int kFaOffXch = kFaOffBar + 256;                // SPLIT: row-maximum / row-sum exchange of the two row owners
+constexpr int kFaSmemBytes = kFaOffXch + 6144;
 constexpr int kFaTmemCols = 512;
 constexpr float kFaRescaleLog2 = 8.0f;             // rescale O only when a row max grows by more than 2^8
 
@@ -60,6 +62,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 
 // bit p set = exponential pair p (of every 16) runs on the FMA pipe; EMU of 16, evenly spaced
 __host__ __device__ constexpr uint32_t fa_emu_mask(int emu) {
+  if (emu < 0) return 0u;
   if (emu == 6) return 0x9249u;  // the pattern attention.cuh uses: both kernels then produce bit-identical results
   uint32_t m = 0;
   for (int p = 0; p < 16; ++p)
@@ -100,8 +103,16 @@ __device__ __forceinline__ FaUnit fa_unit(int idx, const FaArgs& a) {
 // EMU = how many of every 16 exponential pairs are evaluated on the FMA pipe (Cody-Waite + degree-3 polynomial) instead of
 // MUFU.EX2; the kernel is MUFU-bound at head_dim 64 (128 x 128 exponentials per 128-key tile = 1024 MUFU cycles per SM
 // against 512 cycles of MMA), so the split between the two pipes is the tuning knob.
-template <int EMU, bool STAGGER, int WAITP>
-__global__ void __launch_bounds__(kFaThreads, 1)
+// SPLIT: every score row is shared by two threads (64 columns each), 16 softmax warps per CTA = 4 per scheduler, exactly
+// the per-thread arithmetic of attention.cuh (bit-identical results) inside this kernel's persistent two-tile frame. The
+// timing skeleton of the one-thread-per-row version (exponentials replaced by a copy) runs in 0.25 ms of 0.37 ms: with two
+// softmax warps per scheduler a warp's phases (wait, tcgen05.ld, maximum, exponentials, tcgen05.st) are simply serialised;
+// four warps per scheduler let one warp's exponentials (MUFU) overlap the others' fixed-latency phases.
+// Measured (B200, 32 x 1370 x 16 heads): 0.393 ms, against 0.360 ms for one thread per row and 0.350 ms for attention.cuh;
+// bit-identical to both (tools/gpu_check.py attention_impls_agree_*). The pair exchange through shared memory and the 104
+// register cap (a few spills in the exponential loop) cost more than the extra warps hide; kept as impl = 2 for the record.
+template <int EMU, bool STAGGER, int WAITP, bool SPLIT = false>
+__global__ void __launch_bounds__(SPLIT ? kFaThreadsSplit : kFaThreads, 1)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                     const FaArgs a) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
@@ -122,7 +133,9 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   // 7: stagger. Both groups share the MUFU and FMA pipes of their schedulers; started together they run their exponential
   // phases at the same time (each at half rate) and then leave the pipes idle together. Group 1 therefore starts every
   // unit only once group 0 is half way through the exponentials of its first tile; the offset then persists.
-  constexpr int kBarSL = 1, kBarPF = 3, kBarWG = 5, kBarStagger = 7;
+  constexpr int kBarSL = 1, kBarPF = 3, kBarWG = SPLIT ? 13 : 5, kBarStagger = 7;
+  constexpr int kBarPair = 5;                       // SPLIT: 5 + 4 * tile + lane quarter: the two warps that share 32 rows
+  constexpr int kGroupSync = (SPLIT ? 256 : 128) + 32;  // softmax threads of one tile + the issuing warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kv = (a.N + 127) / 128;
@@ -140,7 +153,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       mbar_init(q_free(t), 1);
       mbar_init(s_full(t), 1);
       mbar_init(o_full(t), 1);
-      mbar_init(o_free(t), 4);  // one arrival per warp of the group
+      mbar_init(o_free(t), SPLIT ? 8 : 4);  // one arrival per warp of the group
     }
     for (int s = 0; s < kFaStages; ++s) {
       mbar_init(k_full(s), 1);
@@ -162,7 +175,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if constexpr (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, elected lane per instruction)
     uint32_t qph[2] = {0u, 0u};
@@ -216,7 +229,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       bool kwaited = false;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        if (t == 0 ? sync0 : sync1) named_bar_sync(kBarSL + t, 160);
+        if (t == 0 ? sync0 : sync1) named_bar_sync(kBarSL + t, kGroupSync);
         if (!U.valid[t]) continue;
         if (jj == 0) {
           mbar_wait(q_full(t), qfp[t], 0x630 + t);
@@ -273,7 +286,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         continue;
       }
       for (int j = 0; j < num_kv; ++j) {
-        named_bar_sync(kBarPF + t, 160);  // P_t(j) is in tensor memory (and O_t rescaled if it had to be)
+        named_bar_sync(kBarPF + t, kGroupSync);  // P_t(j) is in tensor memory (and O_t rescaled if it had to be)
         mbar_wait(v_full(vs), vph, 0x650 + vs);
         if (j == 0) {  // the previous unit's epilogue must have read O_t before it is overwritten
           mbar_wait(o_free(t), ofp ^ 1u, 0x660 + t);
@@ -290,6 +303,169 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       }
     }
   }
+  } else if constexpr (SPLIT) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ------------------------------------------------------------------ softmax groups, two threads per query row
+    const int w8 = warp - 4;
+    const int t = w8 >> 3;                 // group = query tile (8 warps each)
+    const int half = (w8 >> 2) & 1;        // which 64 score columns of the row this thread owns
+    const int qd = warp & 3;               // tensor-memory lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const int gthread = threadIdx.x - 128 - 256 * t;  // 0..255 within the group
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tS = tmem_base + 128u * t + lane_off + 64u * half;
+    const uint32_t tO = tmem_base + 256u + 64u * t + lane_off + 32u * half;
+    const uint32_t tP = tmem_base + 384u + 64u * t + lane_off + 32u * half;
+    const uint32_t sO = sbase + kFaOffO + t * kFaTile;
+    float* xm = reinterpret_cast<float*>(fa_smem + kFaOffXch) + t * 768;  // [2 parities][2 halves][128 rows] row maxima
+    float* xl = xm + 512;                                                  // [2 halves][128 rows] row sums
+    const int pair_bar = kBarPair + 4 * t + qd;
+    const float c = a.scale_log2e;
+    uint32_t sfp = 0, ofp = 0;
+    bool stored = false;
+
+    for (int idx = blockIdx.x; idx < a.total_units; idx += gridDim.x) {
+      const FaUnit u = fa_unit(idx, a);
+      if (!u.valid[t]) continue;
+      float m_used = -INFINITY, l_part = 0.f;
+      auto tile = [&](const int j, auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        mbar_wait(s_full(t), sfp, 0x670 + t);
+        sfp ^= 1u;
+        tc_fence_after();
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        named_bar_arrive(kBarSL + t, kGroupSync);  // S_t(j) lives in registers: the issuer may overwrite it with S_t(j+1)
+        if constexpr (MASKED) {  // ragged last tile: keys past N are zero-filled by TMA -> mask them out
+          const int kv_valid = min(128, a.N - j * 128) - half * 64;  // valid keys inside this thread's 64 columns
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_valid) s0[i] = 0xff800000u;
+            if (32 + i >= kv_valid) s1[i] = 0xff800000u;
+          }
+        }
+        float tm[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t* v = (k < 2) ? (s0 + 16 * k) : (s1 + 16 * (k - 2));
+          float x = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+#pragma unroll
+          for (int i = 3; i < 15; i += 2) x = fmax3(x, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          tm[k] = fmaxf(x, __uint_as_float(v[15]));
+        }
+        float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
+        // the two owners of a row combine their partial maxima (double-buffered by tile parity)
+        float* xmj = xm + (j & 1) * 256;
+        xmj[half * 128 + row] = tmax;
+        named_bar_sync(pair_bar, 64);
+        tmax = fmaxf(tmax, xmj[(half ^ 1) * 128 + row]);
+        float sc = 1.0f;
+        bool rescale = false;
+        if (j == 0) {
+          m_used = tmax;
+        } else {
+          const bool grow = (tmax - m_used) * c > kFaRescaleLog2;
+          rescale = __any_sync(0xffffffffu, grow);  // rare; identical in both warps of the pair (same combined maxima)
+          if (rescale) {
+            const float m_new = fmaxf(m_used, tmax);
+            sc = fast_exp2((m_used - m_new) * c);
+            m_used = m_new;
+            l_part *= sc;
+            mbar_wait(o_full(t), ofp, 0x680 + t);  // P_t(j-1) V_{j-1} must have retired before O_t may be rescaled
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {  // this thread's 32 of the row's 64 accumulator columns
+              uint32_t r[8];
+              tmem_ld8(tO + h * 8, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * sc);
+              tmem_st8(tO + h * 8, r);
+            }
+          }
+        }
+        const float mc = m_used * c;
+        constexpr uint32_t kEmuMask = fa_emu_mask(EMU);
+        const uint64_t c2 = f2_pack(c, c), nmc2 = f2_pack(-mc, -mc);
+        uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t pk[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(h ? s1[i] : s0[i]), __uint_as_float(h ? s1[i + 1] : s0[i + 1])), c2, nmc2);
+            float p0, p1;
+            if ((kEmuMask >> (i >> 1)) & 1u) {
+              exp2_fma2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            rs2[(i >> 1) & 3] = f2_add(rs2[(i >> 1) & 3], f2_pack(p0, p1));
+            pk[h * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
+        }
+        {
+          float a0, a1;
+          f2_unpack(f2_add(f2_add(rs2[0], rs2[1]), f2_add(rs2[2], rs2[3])), a0, a1);
+          l_part += a0 + a1;
+        }
+        if (j > 0) {  // P_t(j-1) V_{j-1} must have retired before P_t is overwritten (issued a whole tile ago)
+          if (!rescale) mbar_wait(o_full(t), ofp, 0x680 + t);
+          ofp ^= 1u;
+          tc_fence_after();
+        }
+        tmem_st32(tP, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        named_bar_arrive(kBarPF + t, kGroupSync);  // P_t(j) is in tensor memory
+      };
+#pragma unroll 1
+      for (int j = 0; j < num_kv - 1; ++j) tile(j, FaTag<false>{});
+      if (ragged)
+        tile(num_kv - 1, FaTag<true>{});
+      else
+        tile(num_kv - 1, FaTag<false>{});
+      // ---- epilogue
+      xl[half * 128 + row] = l_part;
+      mbar_wait(o_full(t), ofp, 0x690 + t);  // the last P V of this unit has retired
+      ofp ^= 1u;
+      tc_fence_after();
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.0f / (l_part + xl[(half ^ 1) * 128 + row]);
+      uint32_t o[32];
+      tmem_ld32(tO, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free(t));  // O_t may be overwritten by the next unit's first P V
+      if (gthread == 0 && stored) bulk_wait_read<0>();  // the previous unit's store has finished reading the staging tile
+      named_bar_sync(kBarWG + t, 256);
+      const uint32_t o_row = sO + static_cast<uint32_t>(row) * 128u;
+      const uint32_t o_sw = static_cast<uint32_t>(row & 7);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t chunk = static_cast<uint32_t>(half * 4 + i);
+        st_shared_v4(o_row + ((chunk ^ o_sw) << 4),
+                     pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                     pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                     pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                     pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(kBarWG + t, 256);
+      if (gthread == 0) {
+        tma_store_3d(&tmap_out, sO, u.head * 64, u.q0 + 128 * t, u.img);
+        bulk_commit();
+        stored = true;
+      }
+    }
+    if (gthread == 0 && stored) bulk_wait<0>();
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax groups (one thread = one query row)
@@ -338,7 +514,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         tmem_ld_wait();
         stamp(j, 2);
         tc_fence_before();
-        named_bar_arrive(kBarSL + t, 160);  // S_t(j) lives in registers: the issuer may overwrite it with S_t(j+1)
+        named_bar_arrive(kBarSL + t, kGroupSync);  // S_t(j) lives in registers: the issuer may overwrite it with S_t(j+1)
         const int kv_valid = MASKED ? a.N - j * 128 : 128;  // keys of this tile that exist
         if constexpr (MASKED) {
           // only the 32-column chunks that straddle or lie past N pay for the compare+select pairs (warp-uniform branch)
@@ -416,7 +592,12 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           for (int i = 0; i < 32; i += 2) {
             const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[q][i]), __uint_as_float(s[q][i + 1])), c2, nmc2);
             float p0, p1;
-            if ((kEmuMask >> (i >> 1)) & 1u) {
+            if constexpr (EMU == -1) {  // (bring-up) timing skeleton: exponentials replaced by a copy, wrong results
+              f2_unpack(x2, p0, p1);
+            } else if constexpr (EMU == -2) {  // (bring-up) skeleton without any per-element arithmetic but the pack
+              p0 = __uint_as_float(s[q][i]);
+              p1 = __uint_as_float(s[q][i + 1]);
+            } else if ((kEmuMask >> (i >> 1)) & 1u) {
               exp2_fma2(x2, p0, p1);
             } else {
               float x0, x1;
@@ -424,7 +605,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
-            rs2[q >> 1][(i >> 1) & 3] = f2_add(rs2[q >> 1][(i >> 1) & 3], f2_pack(p0, p1));
+            if constexpr (EMU != -2) rs2[q >> 1][(i >> 1) & 3] = f2_add(rs2[q >> 1][(i >> 1) & 3], f2_pack(p0, p1));
             pk[q][i >> 1] = pack_bf16x2(p0, p1);
           }
           }
@@ -455,7 +636,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         stamp(j, 5);
         tmem_st_wait();
         tc_fence_before();
-        named_bar_arrive(kBarPF + t, 160);  // P_t(j) is in tensor memory
+        named_bar_arrive(kBarPF + t, kGroupSync);  // P_t(j) is in tensor memory
         stamp(j, 6);
       };
 #pragma unroll 1

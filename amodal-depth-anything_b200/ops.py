@@ -72,7 +72,7 @@ def layernorm(x, w, b, eps=1e-6, n_tok=0, drop_cls=False, delta=None, write_x=Fa
 
 
 def attention(qkv, B, N, heads, impl=-1):
-    """impl: -1 = the kernel the model would use at this shape, 0 / 1 = force attention.cuh / attention2.cuh."""
+    """impl: -1 = the kernel the model would use at this shape, 0 / 1 / 2 = force attention.cuh / attention2.cuh (one thread per row) / attention2.cuh (two threads per row)."""
     out = torch.empty(B * N, heads * 64, dtype=torch.bfloat16, device=qkv.device)
     _call(qkv, L.load().ada_op_attention, _p(qkv), _p(out), B, N, heads, impl)
     return out

@@ -73,7 +73,8 @@ int ada_forward(ada_handle h, const float* rgb, const float* const* guides, cons
                 float* out, int32_t B, int32_t H, int32_t W, void* stream);
 /* Bytes of device workspace the handle holds for its largest (B,H,W) so far. */
 size_t ada_workspace_bytes(ada_handle h);
-/* Number of kernels one ada_forward at (B,H,W) launches (for bench.py's gpu_launches). */
+/* Number of kernels the last ada_forward launched (counted while launching; for bench.py's gpu_launches). Pass B = 0 for
+ * "whatever the last forward was", or the shape to make sure it is the one meant; 0 if no forward at that shape has run. */
 int ada_launch_count(ada_handle h, int32_t B, int32_t H, int32_t W);
 /* Test hook: copy a named intermediate of the LAST forward to `dst` (device or host fp32, `count` elements).
  * Names: "tap0".."tap3" ([B,h*w,D] normalised patch tokens, dinov2.py:337-340), "layer1_rn".."layer4_rn",

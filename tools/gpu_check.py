@@ -183,10 +183,15 @@ def chk_attention_impls_agree(B, N, heads, grow=False):
         qkv[:, :, 1] *= ramp.view(1, N, 1, 1)
     qkv = qkv.bfloat16()
     a = ops.attention(qkv, B, N, heads, 0)
-    b = ops.attention(qkv, B, N, heads, 1)
-    torch.cuda.synchronize()
-    diff = (a.float() - b.float()).abs()
-    return {"ok": bool(torch.equal(a, b)), "max_abs": diff.max().item(), "n_diff": int((diff > 0).sum().item()), "n": a.numel()}
+    worst, n_diff, ok = 0.0, 0, True
+    for impl in (1, 2):
+        b = ops.attention(qkv, B, N, heads, impl)
+        torch.cuda.synchronize()
+        diff = (a.float() - b.float()).abs()
+        ok = ok and bool(torch.equal(a, b))
+        worst = max(worst, diff.max().item())
+        n_diff += int((diff > 0).sum().item())
+    return {"ok": ok, "max_abs": worst, "n_diff": n_diff, "n": a.numel()}
 
 
 def chk_layernorm(D, drop):
@@ -400,17 +405,17 @@ CHECKS = {
     "convT_k4_c64_w5_tma": lambda: chk_convT(4, 64, 64, B=3, H=7, W=5, pix=True),
     "convT_k2_c128_w49_tma": lambda: chk_convT(2, 192, 128, B=1, H=37, W=49, pix=True),
     "convT_k2_c256_linear": lambda: chk_convT(2, 256, 256),
-    # both attention kernels on every shape (impl 0 = attention.cuh, 1 = attention2.cuh), then the auto-selected one
-    **{f"attention{i}_small": (lambda i=i: chk_attention(1, 128, 1, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_ragged": (lambda i=i: chk_attention(1, 200, 2, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_1370": (lambda i=i: chk_attention(2, 1370, 6, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_rescale": (lambda i=i: chk_attention(1, 1370, 2, grow=True, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_5477": (lambda i=i: chk_attention(1, 5477, 2, impl=i)) for i in (0, 1)},
+    # both attention kernels on every shape (impl 0 = attention.cuh, 1 / 2 = attention2.cuh one / two threads per row), then the auto-selected one
+    **{f"attention{i}_small": (lambda i=i: chk_attention(1, 128, 1, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_ragged": (lambda i=i: chk_attention(1, 200, 2, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_1370": (lambda i=i: chk_attention(2, 1370, 6, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_rescale": (lambda i=i: chk_attention(1, 1370, 2, grow=True, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_5477": (lambda i=i: chk_attention(1, 5477, 2, impl=i)) for i in (0, 1, 2)},
     # persistent kernel: several work units per CTA, full (two query tiles) and short (one tile) units interleaved
-    **{f"attention{i}_multiunit_1370": (lambda i=i: chk_attention(4, 1370, 16, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_multiunit_300": (lambda i=i: chk_attention(8, 300, 16, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_multiunit_128": (lambda i=i: chk_attention(10, 128, 16, impl=i)) for i in (0, 1)},
-    **{f"attention{i}_multiunit_rescale": (lambda i=i: chk_attention(3, 700, 16, grow=True, impl=i)) for i in (0, 1)},
+    **{f"attention{i}_multiunit_1370": (lambda i=i: chk_attention(4, 1370, 16, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_multiunit_300": (lambda i=i: chk_attention(8, 300, 16, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_multiunit_128": (lambda i=i: chk_attention(10, 128, 16, impl=i)) for i in (0, 1, 2)},
+    **{f"attention{i}_multiunit_rescale": (lambda i=i: chk_attention(3, 700, 16, grow=True, impl=i)) for i in (0, 1, 2)},
     "attention_auto_b32": lambda: chk_attention(32, 1370, 16),
     "attention_impls_agree_1370": lambda: chk_attention_impls_agree(3, 1370, 16),
     "attention_impls_agree_rescale": lambda: chk_attention_impls_agree(2, 700, 16, grow=True),
