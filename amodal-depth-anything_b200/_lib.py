@@ -117,6 +117,9 @@ SIGNATURES = {
                                       c_int32, c_int32, c_void_p]),
     "ada_op_tail_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]),
+    "ada_op_tail_mma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  c_int32, c_int32, c_void_p]),
+    "ada_pack_tail_mma": (c_int32, [c_void_p, c_int32, c_void_p]),
     "ada_pack_tail_taps": (c_int32, [c_void_p, c_int32, c_void_p]),
     "ada_pack_conv3x3": (c_int32, [c_void_p, c_int32, c_int32, c_void_p]),
     "ada_pack_convT": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),

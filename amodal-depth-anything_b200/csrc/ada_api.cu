@@ -26,6 +26,7 @@
 #include "evalops.cuh"
 #include "gemm.cuh"
 #include "pack.cuh"
+#include "tail_mma.cuh"
 #include "tma_host.h"
 
 namespace ada {
@@ -649,6 +650,46 @@ static void launch_tail_gather(const __half* V, const float* bias2, const float*
   ++g_launches;
 }
 
+// Tail on tensor cores (tail_mma.cuh): the fp16 output_conv1 map in, the fp32 result out.
+static bool tail_mma_supported(int C, int Hl, int Wl, int H, int W) {
+  return C % 32 == 0 && C <= kTmMaxC && Hl * 14 == H * 8 && Wl * 14 == W * 8 && W % kTmTileW == 0;
+}
+static void launch_tail_mma(const __half* L, const __half* wpk, const float* bias2, const float* aux, float* out, int B,
+                            int Hl, int Wl, int H, int W, int C, int sigmoid, cudaStream_t st) {
+  ADA_REQUIRE(tail_mma_supported(C, Hl, Wl, H, W), "tail_mma: C % 32 == 0, C <= 128, 8h -> 14h geometry");
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(tail_mma_kernel, tm_smem_bytes(kTmMaxC), attr_done);
+  uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Wl), static_cast<uint64_t>(Hl), static_cast<uint64_t>(B)};
+  uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Wl) * C * 2, static_cast<uint64_t>(Hl) * Wl * C * 2};
+  uint32_t box[4] = {static_cast<uint32_t>(C), kTmPatchW, kTmPatchH, 1};
+  const CUtensorMap tl = make_tmap_bf16(L, 4, dims, str, box, nullptr, false);  // 2-byte elements, dense box
+  TailMmaArgs a;
+  a.wpk = wpk;
+  a.bias2 = bias2;
+  a.aux = aux;
+  a.out = out;
+  a.B = B;
+  a.Hl = Hl;
+  a.Wl = Wl;
+  a.H = H;
+  a.W = W;
+  a.C = C;
+  a.sigmoid = sigmoid;
+  a.tiles_x = W / kTmTileW;
+  a.tiles_y = (H + kTmTileH - 1) / kTmTileH;
+  a.total_tiles = B * a.tiles_x * a.tiles_y;
+  ADA_REQUIRE(static_cast<long long>(a.total_tiles) * std::max(a.tiles_x, a.tiles_y) < (1LL << 31), "tail_mma: too many tiles");
+  a.magic_x = static_cast<uint32_t>(((1ULL << 32) + a.tiles_x - 1) / a.tiles_x);
+  a.magic_y = static_cast<uint32_t>(((1ULL << 32) + a.tiles_y - 1) / a.tiles_y);
+  const int grid = std::min(a.total_tiles, device_info().sms);
+  // tensor-bound by construction, reported with the conv FLOPs of the layer it replaces (dpt.py:195: 3x3, C -> 32, at H x W)
+  ProfScope prof(PC_TAIL_GATHER, 2.0 * B * static_cast<double>(H) * W * 32.0 * 9.0 * C,
+                 static_cast<double>(B) * (2.0 * Hl * Wl * C + 4.0 * H * W), st);
+  launch_pdl(tail_mma_kernel, dim3(grid), dim3(kTmThreads), static_cast<size_t>(tm_smem_bytes(C)), st, tl, a);
+  ADA_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+}
+
 static void launch_patch_gather(const float* rgb, const float* const* guides, const int* guide_ch, int n_guides,
                                 __nv_bfloat16* out, int B, int H, int W, int Kpad, int normalize, cudaStream_t st) {
   ADA_REQUIRE(n_guides >= 0 && n_guides <= 3, "at most 3 guide tensors");
@@ -783,6 +824,7 @@ struct ada_model {
   RefineW ref[5];  // 1..4
   ConvW oc1, oc2;
   __nv_bfloat16* w_tail_taps = nullptr;  // [288, F/2]
+  __half* w_tail_mma = nullptr;          // [3][F/16][96][8] fp16 (tail_mma_kernel), null when F/2 is not supported there
   float* tail_aux = nullptr;  // 32 weights + 1 bias of output_conv2.2
 
   // per-(H,W) position cache on device
@@ -1130,6 +1172,13 @@ static void finalize_model(ada_model* m) {
     m->w_tail_taps = dev_alloc<__nv_bfloat16>(m, n);
     run_pack(t, nullptr, m->w_tail_taps, n, PackDesc{PACK_TAIL, F / 2, 0, 0, 0});
   }
+  if ((F / 2) % 32 == 0 && F / 2 <= kTmMaxC) {
+    const float* t = need(m, hd + "scratch.output_conv2.0.weight", {32, F / 2, 3, 3});
+    const int n = 288 * (F / 2);
+    m->w_tail_mma = dev_alloc<__half>(m, n);
+    pack_tail_mma_kernel<<<(n + 255) / 256, 256>>>(t, m->w_tail_mma, F / 2);
+    ADA_CHECK_CUDA(cudaGetLastError());
+  }
   m->oc2 = up_conv3x3(m, hd + "scratch.output_conv2.0", 32, F / 2, true);
   {
     const std::vector<float> w2 = need_host(m, hd + "scratch.output_conv2.2.weight", {1, 32, 1, 1});
@@ -1290,7 +1339,8 @@ static void ensure_workspace(ada_model* m, int B, int H, int W, cudaStream_t st)
 
 // conv3x3 (pad 1, stride 1) over NHWC bf16 through the implicit-GEMM path
 static void conv3x3(const __nv_bfloat16* in, int B, int H, int W, const ConvW& cw, int act, const __nv_bfloat16* r1,
-                    const __nv_bfloat16* r2, __nv_bfloat16* out, __nv_bfloat16* out_relu, cudaStream_t st, int force_cg = 0) {
+                    const __nv_bfloat16* r2, __nv_bfloat16* out, __nv_bfloat16* out_relu, cudaStream_t st, int force_cg = 0,
+                    int epi = EPI_BF16) {
   GemmLaunch L;
   L.force_cg = force_cg;
   L.A = in;
@@ -1303,7 +1353,7 @@ static void conv3x3(const __nv_bfloat16* in, int B, int H, int W, const ConvW& c
   L.H = H;
   L.W = W;
   L.Cin = cw.cin;
-  L.args.epi = EPI_BF16;
+  L.args.epi = epi;
   L.args.act = act;
   L.args.bias = cw.b;
   L.args.resid1 = r1;
@@ -1583,8 +1633,17 @@ static void forward_body(ada_model* m, const float* rgb, const float* const* gui
   }
   // output_conv1 -> bilinear to (H, W) -> output_conv2 (conv3x3 + ReLU + 1x1 + Sigmoid) (dpt.py:193-195)
   static const int oc1_cg = env_int("ADA_OC1_CG", 0);
-  conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st, oc1_cg);
-  if (tail_fused(ph[1], pw[1], H, W)) {
+  // tail_mma_kernel (upsample + output_conv2 on tensor cores, one kernel) wherever its geometry and channel count allow;
+  // ADA_TAIL_MMA=0 selects the older tap-GEMM + gather pair, which also serves F/2 > 128 (ViT-G heads)
+  static const int tail_mma_env = env_int("ADA_TAIL_MMA", 1);
+  const bool tail_mma = tail_mma_env && m->w_tail_mma != nullptr && tail_mma_supported(F / 2, ph[1], pw[1], H, W) &&
+                        tail_fused(ph[1], pw[1], H, W);
+  conv3x3(m->path[1], B, ph[1], pw[1], m->oc1, ACT_NONE, nullptr, nullptr, m->oc1b, nullptr, st, oc1_cg,
+          tail_mma ? EPI_F16 : EPI_BF16);
+  if (tail_mma) {
+    launch_tail_mma(reinterpret_cast<const __half*>(m->oc1b), m->w_tail_mma, m->oc2.b, m->tail_aux, out, B, ph[1], pw[1], H, W,
+                    F / 2, c.sigmoid, st);
+  } else if (tail_fused(ph[1], pw[1], H, W)) {
     GemmArgs e{};
     e.epi = EPI_F16;  // the tap map is stored as fp16 (tail_gather_kernel interpolates it with packed fp16 FMAs)
     e.out_bf16 = m->vtap;
@@ -2086,6 +2145,33 @@ int ada_op_tail_gather(const void* v_f16, const float* bias2, const float* aux, 
     require_device();
     launch_tail_gather(static_cast<const __half*>(v_f16), bias2, aux, out, B, Hl, Wl, H, W, sigmoid,
                        static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_op_tail_mma(const void* l_f16, const void* wpk_f16, const float* bias2, const float* aux, float* out, int32_t B,
+                    int32_t Hl, int32_t Wl, int32_t H, int32_t W, int32_t C, int32_t sigmoid, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_tail_mma(static_cast<const __half*>(l_f16), static_cast<const __half*>(wpk_f16), bias2, aux, out, B, Hl, Wl, H, W,
+                    C, sigmoid, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ada_pack_tail_mma(const float* w_host, int32_t C, void* dst_f16) {
+  return guarded([&] {
+    require_device();
+    ADA_REQUIRE(w_host && dst_f16 && C % 32 == 0 && C <= kTmMaxC, "ada_pack_tail_mma: C % 32 == 0, C <= 128");
+    float* tmp = nullptr;
+    const size_t n = static_cast<size_t>(288) * C;
+    ADA_CHECK_CUDA(cudaMalloc(&tmp, n * 4));
+    cudaError_t e = cudaMemcpy(tmp, w_host, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      pack_tail_mma_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(tmp, static_cast<__half*>(dst_f16), C);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cudaFree(tmp);
+    ADA_CHECK_CUDA(e);
   });
 }
 

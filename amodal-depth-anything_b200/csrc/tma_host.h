@@ -30,8 +30,9 @@ inline PFN_tmapEncodeTiled get_encode_fn() {
 // bf16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides in BYTES for dims 1..rank-1.
 // elem_strides (optional): traversal stride per dimension; a box of `box[i]` tensor elements then delivers
 // ceil(box[i] / elem_strides[i]) elements (every elem_strides[i]-th one) -- the stride-2 implicit-GEMM convolution.
+// swizzle128 = false: dense (un-swizzled) box, inner box dimension up to 256 elements.
 inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                  const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+                                  const uint32_t* box, const uint32_t* elem_strides = nullptr, bool swizzle128 = true) {
   CUtensorMap m;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -45,7 +46,7 @@ inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* di
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                                const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string msg = "cuTensorMapEncodeTiled failed: code " + std::to_string(static_cast<int>(r)) + " rank " +

@@ -138,6 +138,23 @@ def tail_gather(V, bias2, aux, H, W, sigmoid=True):
     return out
 
 
+def pack_tail_mma(w):
+    """output_conv2.0 weight [32,C,3,3] -> fp16 [3, C/8, 96, 8] on cuda (the B operand of tail_mma_kernel)."""
+    C = w.shape[1]
+    wh = w.detach().float().cpu().contiguous()
+    out = torch.empty(3, C // 8, 96, 8, dtype=torch.float16, device="cuda")
+    L.check(L.load().ada_pack_tail_mma(_p(wh), C, _p(out)))
+    return out
+
+
+def tail_mma(Lmap, wpk, bias2, aux, H, W, sigmoid=1):
+    """Lmap: NHWC fp16 [B,Hl,Wl,C] (output_conv1 map) -> fp32 [B,H,W]: upsample + output_conv2 in one kernel."""
+    B, Hl, Wl, C = Lmap.shape
+    out = torch.empty(B, H, W, dtype=torch.float32, device=Lmap.device)
+    _call(Lmap, L.load().ada_op_tail_mma, _p(Lmap), _p(wpk), _p(bias2), _p(aux), _p(out), B, Hl, Wl, H, W, C, int(sigmoid))
+    return out
+
+
 # ---- single-image pre/post-processing of infer.py (include/amodal_b200.h, "row f2")
 def image_nearest(img_u8_hwc, H=518, W=518, normalize=False):
     """uint8 [H0,W0,3] (device) -> fp32 [1,3,H,W]; infer.py:84-86 (normalize=True: infer.py:18)."""

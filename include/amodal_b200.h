@@ -191,6 +191,14 @@ int ada_op_patch_gather(const float* rgb, const float* const* guides, const int3
  * aux = [w3 (32), b3]. Requires the 8h -> 14h geometry (Hl*14 == H*8). */
 int ada_op_tail_gather(const void* v_f16, const float* bias2, const float* aux, float* out, int32_t B, int32_t Hl, int32_t Wl,
                        int32_t H, int32_t W, int32_t sigmoid, void* stream);
+/* Tail on tensor cores, one kernel (dpt.py:194-195): l_f16 = the output_conv1 map, NHWC fp16 [B,Hl,Wl,C] (conv with
+ * epi = 10); bilinear 8h -> 14h upsample (align_corners), conv3x3(C -> 32) with zero padding as a tcgen05 GEMM over
+ * upsampled tiles built in shared memory, ReLU, 1x1 conv, sigmoid (1) / ReLU (2) / nothing (0); out fp32 [B,H,W].
+ * wpk_f16 from ada_pack_tail_mma; aux = [w3 (32), b3]. Requires C % 32 == 0, C <= 128, Hl*14 == H*8, W % 14 == 0. */
+int ada_op_tail_mma(const void* l_f16, const void* wpk_f16, const float* bias2, const float* aux, float* out, int32_t B,
+                    int32_t Hl, int32_t Wl, int32_t H, int32_t W, int32_t C, int32_t sigmoid, void* stream);
+/* output_conv2.0 weight [32,C,3,3] (host fp32) -> [ky][C/8][kx*32+co][8] fp16 on the device (288*C elements). */
+int ada_pack_tail_mma(const float* w_host, int32_t C, void* dst_dev_f16);
 /* output_conv2.0 weight [32,Cm,3,3] (host fp32) -> [(tap*32+co), Cm] bf16 on the device. */
 int ada_pack_tail_taps(const float* w_host, int32_t Cm, void* dst_dev_bf16);
 /* Weight packers (host fp32 in, device bf16 out) -- the same code ada_finalize uses. */

@@ -316,6 +316,27 @@ def chk_fused_tail(gh, gw):
     return _cmp("fused_tail", out, ref, 5e-3, 0)
 
 
+def chk_tail_mma(gh, gw, Cm=64, B=2, sigmoid=1):
+    """upsample + output_conv2 on tensor cores (tail_mma_kernel) == conv2(interp(y)) chain of dpt.py:194-195."""
+    torch, L, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(19)
+    Hl, Wl, H, W = 8 * gh, 8 * gw, 14 * gh, 14 * gw
+    y = (torch.randn(B, Cm, Hl, Wl, generator=g, device="cuda") * 1.5).half()
+    w2 = torch.randn(32, Cm, 3, 3, generator=g, device="cuda") * (1.0 / (3 * Cm ** 0.5))
+    b2 = torch.randn(32, generator=g, device="cuda") * 0.1
+    w3 = torch.randn(32, generator=g, device="cuda") * 0.3
+    b3 = torch.randn(1, generator=g, device="cuda") * 0.1
+    up = torch.nn.functional.interpolate(y.float(), (H, W), mode="bilinear", align_corners=True)
+    z = torch.relu(torch.nn.functional.conv2d(up, w2.half().float(), b2, padding=1))
+    ref = (z * w3.view(1, 32, 1, 1)).sum(1) + b3
+    ref = torch.sigmoid(ref) if sigmoid == 1 else torch.relu(ref) if sigmoid == 2 else ref
+    wpk = ops.pack_tail_mma(w2)
+    ya = y.permute(0, 2, 3, 1).contiguous()
+    out = ops.tail_mma(ya, wpk, b2, torch.cat([w3, b3]).contiguous(), H, W, sigmoid)
+    torch.cuda.synchronize()
+    return _cmp("tail_mma", out, ref, 5e-3, 0)
+
+
 def chk_patch_gather():
     torch, L, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(9)
@@ -436,6 +457,11 @@ CHECKS = {
     "channel_ln_1536": lambda: chk_channel_ln(1536),
     "fused_tail_5x7": lambda: chk_fused_tail(5, 7),
     "fused_tail_9x9": lambda: chk_fused_tail(9, 9),
+    "tail_mma_5x7_c64": lambda: chk_tail_mma(5, 7, 64),
+    "tail_mma_9x9_c128": lambda: chk_tail_mma(9, 9, 128),
+    "tail_mma_3x11_c32_logit": lambda: chk_tail_mma(3, 11, 32, B=3, sigmoid=0),
+    "tail_mma_37x37_c128": lambda: chk_tail_mma(37, 37, 128, B=2),
+    "tail_mma_1x1_c64_relu": lambda: chk_tail_mma(1, 1, 64, B=5, sigmoid=2),
     "patch_gather": chk_patch_gather,
     "conv_chln_256": lambda: chk_conv(2, 37, 45, 256, 256, "chln"),
     "conv_chln_256_cg2": lambda: chk_conv(2, 40, 70, 256, 256, "chln", cg=2),
