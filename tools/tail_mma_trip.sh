@@ -2,13 +2,6 @@
 # One GPU-box visit for the tensor-core tail: operator parity (both descriptor field orders on the first visit), model parity, timing.
 mkdir -p gpurun_out
 timeout 600 python tools/gpu_check.py --only tail_mma --out gpurun_out/tail_mma_check.json 2>&1 | tail -12
-if [ -n "$SWAP" ]; then
-timeout 300 python - <<'PY' 2>&1 | tail -5
-import sys; sys.path.insert(0, "tools")
-import gpu_check
-print("swap=1", gpu_check.chk_tail_mma(5, 7, 64, swap=1))
-PY
-fi
 echo "=== model parity (golden + bench-path tests)"
 timeout 1500 python -m pytest tests/test_forward_gpu.py tests/test_bench_paths_gpu.py tests/test_raw_gpu.py -x -q 2>&1 | tail -5
 echo "=== bench"
