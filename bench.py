@@ -107,6 +107,64 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class NvmlSampler:
+    """Same report as ClockSampler, sampled in-process through NVML (pynvml) from a thread every 50 ms: three light
+    queries (SM clock, power, clocks-event reasons) instead of an nvidia-smi process that re-queries the device in a
+    loop."""
+
+    def __init__(self, uuid):
+        self.uuid, self.rows, self.ok = uuid, [], False
+        self.t_begin, self.t_end, self._stop = None, None, threading.Event()
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+            self.smax = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def _run(self):
+        N = self.N
+        while not self._stop.is_set():
+            try:
+                self.rows.append((time.time(), float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)),
+                                  N.nvmlDeviceGetPowerUsage(self.h) / 1e3,
+                                  int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        N = self.N
+        bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+        t0 = self.t_begin or 0.0
+        t1 = (self.t_end or time.time()) + 0.05
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        reasons = sorted(n for n, b in bits.items() if any(r[3] & b for r in rows))
+        return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "sm_max_mhz": self.smax,
+                "power_w_max": max([r[2] for r in rows]) if rows else None, "samples": len(rows), "reasons": reasons,
+                "how": "in-process NVML, 50 ms"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU / reference legs
 def cpu_reference_rate(encoder, size, steps, warmup):
     """Times the oracle (CPU restatement of the reference forward) on all host cores: `steps` images, ONE image per step."""
@@ -204,19 +262,23 @@ def make_inputs(torch, B, H, W, dev, seed):
     return x, mask, obs
 
 
-def timed_loop(torch, fn, steps, warmup, barrier):
-    """W untimed calls, then K calls between two CUDA events on the current stream, barrier + synchronize on both sides."""
+def timed_loop(torch, fn, steps, warmup, barrier, per_step=None):
+    """W untimed calls, then K calls between two CUDA events on the current stream, barrier + synchronize on both sides.
+    The reported time is (last event - first event) / K; `per_step` (a list) additionally receives the K step durations
+    from events recorded between the steps, so that an outlier step is visible in the JSON line."""
     out = None
     for _ in range(warmup):
         out = fn()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         out = fn()
-    e1.record()
+        ev[i + 1].record()
     barrier()
-    return e0.elapsed_time(e1) / steps, out
+    if per_step is not None:
+        per_step.extend(round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps))
+    return ev[0].elapsed_time(ev[steps]) / steps, out
 
 
 def parity_check(torch, model, x, mask, obs, out, idx=0):
@@ -345,9 +407,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
-    if sampler:
+    sampler = None
+    if rank == 0:  # in-process NVML; the nvidia-smi loop only where pynvml is missing
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+        sampler = NvmlSampler(uuid)
         sampler.start()
+        if not sampler.ok:
+            sampler = ClockSampler(uuid)
+            sampler.start()
     for _ in range(a.warmup):
         out = step()
     barrier()
@@ -357,7 +424,8 @@ def main():
     barrier()
     if sampler:
         sampler.mark_begin()
-    ms, out = timed_loop(torch, step, a.steps, 0, barrier)
+    step_ms = []
+    ms, out = timed_loop(torch, step, a.steps, 0, barrier, step_ms)
     if sampler:
         sampler.mark_end()
     clocks = sampler.stop() if sampler else None
@@ -508,7 +576,7 @@ def main():
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "dtype": "bf16", "data": "synthetic", "config": cfg, "ms_steps_rank0": step_ms,
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms, "same_result_as_device_timed_call": e2e_same,
                     "how": "StreamedInference: pinned host -> H2D -> AmodalDAv2.forward -> D2H per step, copies on side streams"},
