@@ -418,9 +418,12 @@ def main():
     for _ in range(a.warmup):
         out = step()
     barrier()
-    time.sleep(0.3)  # (all ranks) let nvidia-smi finish starting up outside the timed region
-    for _ in range(2):
+    # more untimed steps until the device has been under load for ~1.5 s: on some boxes of the pool the first second of a
+    # process showed single steps stalling by 20-40 ms (power management settling; `ms_steps_rank0` makes such a step visible)
+    t_w = time.time()
+    while time.time() - t_w < 1.5:
         out = step()
+        torch.cuda.synchronize()
     barrier()
     if sampler:
         sampler.mark_begin()

@@ -26,24 +26,36 @@ def per_step(n, label):
     print(f"{label:28s} mean {sum(ms)/n:6.2f}  " + " ".join(f"{m:5.1f}" for m in ms), flush=True)
 
 
+def per_step(n, label):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(n):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+    print(f"{label:28s} mean {sum(ms)/n:6.2f}  median {ms[n//2]:6.2f}  max3 " + " ".join(f"{m:5.1f}" for m in ms[-3:]), flush=True)
+
+
+N = int(os.environ.get("N", "30"))
 for _ in range(3):
     step()
-per_step(10, "no sampler (first)")
 uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
-s = bench.ClockSampler(uuid)
-s.start()
-time.sleep(0.5)
-s.mark_begin()
-per_step(10, "nvidia-smi -lms 100")
-s.mark_end()
-print("   ", s.stop(), flush=True)
-per_step(10, "no sampler (after smi)")
-if hasattr(bench, "NvmlSampler"):
+for rep in range(2):
+    per_step(N, "no sampler")
     s = bench.NvmlSampler(uuid)
     s.start()
     time.sleep(0.3)
     s.mark_begin()
-    per_step(10, "in-process NVML 50 ms")
+    per_step(N, "in-process NVML 50 ms")
     s.mark_end()
     print("   ", s.stop(), flush=True)
-    per_step(10, "no sampler (after nvml)")
+    per_step(N, "no sampler")
+    s = bench.ClockSampler(uuid)
+    s.start()
+    time.sleep(1.0)
+    s.mark_begin()
+    per_step(N, "nvidia-smi -lms 100")
+    s.mark_end()
+    print("   ", s.stop(), flush=True)
