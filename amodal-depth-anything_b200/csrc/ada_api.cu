@@ -230,6 +230,36 @@ struct ProfScope {
   }
 };
 
+// Pixel-tile shape of an implicit-GEMM conv launch: 2^lw x 2^lh pixels of 2^lb images (128 A rows per CTA; a CTA pair puts two
+// tiles side by side in x). Picks the shape with the fewest padded pixels over (batch, H, W); ties keep the 16 x 8 x 1 default,
+// then prefer tiles that span fewer images and more of a row (DRAM locality of the TMA boxes). Every shape accumulates an
+// output element over (tap, channel) in the same order, so the choice -- which depends on the batch -- never changes a bit.
+struct TileGeo {
+  int lw = 4, lh = 3, lb = 0;
+  long long padded = 0;  // pixels computed, padding included
+};
+static TileGeo pick_tile_geo(int B, int H, int W, int cg, bool general) {
+  auto cost = [&](int lw, int lh, int lb) {
+    const long long tw = (1LL << lw) * cg, th = 1LL << lh, nb = 1LL << lb;
+    return ((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) * ((B + nb - 1) / nb * nb);
+  };
+  TileGeo best;
+  best.padded = cost(4, 3, 0);
+  if (!general) return best;
+  for (int lw = 5; lw >= 1; --lw)        // 2 .. 32 pixels wide: a warp's 32 accumulator rows are whole tile rows
+    for (int lh = 7 - lw; lh >= 0; --lh) {
+      const int lb = 7 - lw - lh;
+      const long long c = cost(lw, lh, lb);
+      if (c < best.padded) {  // strict: earlier candidates (wider, taller, fewer images) win ties
+        best.lw = lw;
+        best.lh = lh;
+        best.lb = lb;
+        best.padded = c;
+      }
+    }
+  return best;
+}
+
 static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   GemmArgs g = L.args;
   g.M = L.M;
@@ -250,6 +280,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
   ADA_REQUIRE(bn != 32 || g.epi == EPI_TAIL, "BN=32 is only built for the fused tail epilogue");
   ADA_REQUIRE(g.epi != EPI_SWIGLU || L.N % 128 == 0, "SwiGLU needs N % 128 == 0");
   ADA_REQUIRE(L.ldb % 8 == 0, "weight pitch must be a multiple of 8 elements");
+  // general pixel-tile shapes: 3x3 convs whose epilogue stores through the 4-D output map (ADA_CONV_GEO=0: 16 x 8 x 1 only)
+  static const int conv_geo_env = env_int("ADA_CONV_GEO", 1);
+  const bool conv_geo_general = conv_geo_env != 0 && L.a_mode == A_CONV3X3 && L.conv_taps == 9 &&
+                                (g.epi == EPI_BF16 || g.epi == EPI_F16 || g.epi == EPI_BF16_CHLN);
   // ---- CTA pairs (cta_group::2) when the problem is big enough to keep 74 pairs busy and pairing wastes little
   int cg = 1;
   {
@@ -258,8 +292,9 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     const int tiles_n_ = (L.N + bn - 1) / bn;
     bool ok = (bn == 256 || (want == 2 && bn == 128 && g.epi == EPI_BF16)) && g.epi != EPI_TAIL;  // N=128 pairs are smem-read bound (A 4 KB + B 2 KB / 32 clk)
     if (ok && L.a_mode == A_CONV3X3) {
-      const int pad1 = (L.W + kTileW - 1) / kTileW * kTileW, pad2 = (L.W + 2 * kTileW - 1) / (2 * kTileW) * 2 * kTileW;
-      const long long pairs = static_cast<long long>(L.batch) * ((L.H + kTileH - 1) / kTileH) * (pad2 / (2 * kTileW)) * tiles_n_;
+      const long long pad1 = pick_tile_geo(L.batch, L.H, L.W, 1, conv_geo_general).padded;
+      const long long pad2 = pick_tile_geo(L.batch, L.H, L.W, 2, conv_geo_general).padded;
+      const long long pairs = pad2 / (2 * kBlockM) * tiles_n_;
       if (want != 2) ok = (pad2 * 100 <= pad1 * 107) && pairs >= 2 * (device_info().sms / 2);
     } else if (ok) {
       const long long pairs = static_cast<long long>((L.M + 2 * kBlockM - 1) / (2 * kBlockM)) * tiles_n_;
@@ -300,8 +335,14 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
     ADA_REQUIRE(L.Cin % 8 == 0, "conv Cin must be a multiple of 8");
     g.H = L.H;
     g.W = L.W;
-    g.tiles_x = (L.W + kTileW * cg - 1) / (kTileW * cg);
-    g.tiles_y = (L.H + kTileH - 1) / kTileH;
+    const TileGeo geo = pick_tile_geo(L.batch, L.H, L.W, cg, conv_geo_general);
+    g.lw = geo.lw;
+    g.lh = geo.lh;
+    g.lb = geo.lb;
+    const int tw = 1 << geo.lw, th = 1 << geo.lh, nb = 1 << geo.lb;
+    g.tiles_x = (L.W + tw * cg - 1) / (tw * cg);
+    g.tiles_y = (L.H + th - 1) / th;
+    g.tiles_b = (L.batch + nb - 1) / nb;
     g.c_chunks = round_up(L.Cin, kBlockK) / kBlockK;
     g.K = L.conv_taps * g.c_chunks * kBlockK;
     const int sd = L.conv_stride;
@@ -315,10 +356,10 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
                         static_cast<uint64_t>(L.batch)};
     uint64_t str[3] = {static_cast<uint64_t>(L.Cin) * 2, static_cast<uint64_t>(Win) * L.Cin * 2,
                        static_cast<uint64_t>(Hin) * Win * L.Cin * 2};
-    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(kTileW * sd), static_cast<uint32_t>(kTileH * sd), 1};
+    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(tw * sd), static_cast<uint32_t>(th * sd), static_cast<uint32_t>(nb)};
     uint32_t es[4] = {1, static_cast<uint32_t>(sd), static_cast<uint32_t>(sd), 1};
     ta = make_tmap_bf16(L.A, 4, dims, str, box, es);
-    tiles_m = L.batch * g.tiles_x * g.tiles_y;
+    tiles_m = g.tiles_b * g.tiles_x * g.tiles_y;
     ADA_REQUIRE(L.M == L.batch * L.H * L.W, "conv M mismatch");
   } else {
     ADA_REQUIRE(L.lda % 8 == 0, "A pitch must be a multiple of 8 elements");
@@ -349,7 +390,9 @@ static void launch_gemm(const GemmLaunch& L, cudaStream_t st) {
                             static_cast<uint64_t>(L.batch)};
         uint64_t str[3] = {static_cast<uint64_t>(n_out) * 2, static_cast<uint64_t>(L.W) * n_out * 2,
                            static_cast<uint64_t>(L.H) * L.W * n_out * 2};
-        uint32_t box[4] = {64, kTileW, 2, 1};
+        // one epilogue warp = 32 consecutive accumulator rows = whole tile rows (and whole images of the tile if it is small)
+        const int srows = std::min(1 << g.lh, 32 >> g.lw), simgs = std::max(1, 32 >> (g.lw + g.lh));
+        uint32_t box[4] = {64, static_cast<uint32_t>(1 << g.lw), static_cast<uint32_t>(srows), static_cast<uint32_t>(simgs)};
         return make_tmap_bf16(ptr, 4, dims, str, box);
       }
       return make_tmap_2d(ptr, static_cast<uint64_t>(n_out), static_cast<uint64_t>(L.M), static_cast<uint64_t>(g.ldo), 64, 32);

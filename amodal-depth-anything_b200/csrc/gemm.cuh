@@ -91,6 +91,11 @@ struct GemmArgs {
   int epi, act;
   // conv geometry (A_CONV3X3) -- also used by EPI_CONVT for the input grid
   int H, W, tiles_x, tiles_y, c_chunks;  // OUTPUT map size; c_chunks = c_pad / 64
+  // A_CONV3X3 M tile = 2^lw x 2^lh pixels of 2^lb consecutive images (lw + lh + lb = 7; 16 x 8 x 1 by default): the shape is
+  // picked per launch to minimise the padding of the (H, W, batch) extents -- 8 x 16 tiles pad a 37 x 37 map by 1.40x and a
+  // 19 x 19 one by 2.13x, 2 x 2 pixels x 32 images pad them by 1.05x / 4 x 4 x 8 by 1.11x. tiles_x counts tiles of 2^lw * CG
+  // pixels, tiles_b groups of 2^lb images. The accumulation order of an output element does not depend on the shape.
+  int lw, lh, lb, tiles_b;
   int conv_taps;        // A_CONV3X3 (pixel-tile A operand): 9 = 3x3 conv, 1 = pointwise (k == s transposed conv, EPI_CONVT)
   int conv_stride;      // A_CONV3X3: 1, or 2 (resize_layers[3], dpt.py:102-107): input pixel = stride * output pixel + tap - 1
   // epilogue operands
@@ -232,7 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // A tile = CG stacked 128-row sub-tiles (linear) or CG horizontally adjacent 8x16 pixel patches (conv; g.tiles_x
   // already counts 16*CG-pixel wide tiles). Work unit = CTA pair when CG == 2.
   const int tiles_n = (g.N + BN - 1) / BN;
-  const int tiles_m = (g.a_mode == A_CONV3X3) ? (g.M / (g.H * g.W)) * g.tiles_x * g.tiles_y
+  const int tiles_m = (g.a_mode == A_CONV3X3) ? g.tiles_b * g.tiles_x * g.tiles_y
                                               : (g.M + kBlockM * CG - 1) / (kBlockM * CG);
   const int num_tiles = tiles_m * tiles_n;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
@@ -255,10 +260,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int img = 0, y0 = 0, x0 = 0;
       if (g.a_mode == A_CONV3X3) {
         const int per_img = g.tiles_x * g.tiles_y;
-        img = mt / per_img;
+        img = (mt / per_img) << g.lb;
         const int r = mt % per_img;
-        y0 = (r / g.tiles_x) * kTileH;
-        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) * kTileW;
+        y0 = (r / g.tiles_x) << g.lh;
+        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) << g.lw;
       }
       const int m_row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM;
       const int n_row0 = nt * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
@@ -379,15 +384,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int img = 0, y0 = 0, x0 = 0;
       if (g.a_mode == A_CONV3X3) {
         const int per_img = g.tiles_x * g.tiles_y;
-        img = mt / per_img;
+        img = (mt / per_img) << g.lb;
         const int r = mt % per_img;
-        y0 = (r / g.tiles_x) * kTileH;
-        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) * kTileW;
-        const int y = y0 + row / kTileW;
-        const int x = x0 + row % kTileW;
-        valid = (y < g.H) && (x < g.W);
-        orow = (static_cast<long long>(img) * g.H + y) * g.W + x;
+        y0 = (r / g.tiles_x) << g.lh;
+        x0 = ((r % g.tiles_x) * CG + static_cast<int>(cta_rank)) << g.lw;
+        // accumulator row -> (image, y, x) inside the tile: x fastest, then y, then image -- the order the TMA box delivered
+        const int x = x0 + (row & ((1 << g.lw) - 1));
+        const int y = y0 + ((row >> g.lw) & ((1 << g.lh) - 1));
+        const int ib = img + (row >> (g.lw + g.lh));
+        valid = (y < g.H) && (x < g.W) && (static_cast<long long>(ib) * g.H * g.W < g.M);
+        orow = (static_cast<long long>(ib) * g.H + y) * g.W + x;
         m = static_cast<int>(orow);
+        // this warp's 32 rows form the box {2^lw, min(2^lh, 32 >> lw), 32 >> (lw + lh) or 1} of the output map, starting at:
+        y0 += ((q * 32) >> g.lw) & ((1 << g.lh) - 1);
+        img += (q * 32) >> (g.lw + g.lh);
       } else {
         m = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + row;
         valid = m < g.M;
@@ -528,7 +538,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             fence_proxy_async_smem();
             __syncwarp();
             if (g.a_mode == A_CONV3X3)
-              tma_store_4d_commit_w(&tmap_c, buf, oc, x0, y0 + 2 * q, img);
+              tma_store_4d_commit_w(&tmap_c, buf, oc, x0, y0, img);
             else
               tma_store_2d_commit_w(&tmap_c, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
             if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
@@ -643,7 +653,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               {  // whole warp converged, elected lane issues store + commit (no uniform-register waterfall)
                 const CUtensorMap* tm = (pass == 0) ? &tmap_c : &tmap_c2;
                 if (g.a_mode == A_CONV3X3)
-                  tma_store_4d_commit_w(tm, buf, oc, x0, y0 + 2 * q, img);
+                  tma_store_4d_commit_w(tm, buf, oc, x0, y0, img);
                 else
                   tma_store_2d_commit_w(tm, buf, oc, (mt * CG + static_cast<int>(cta_rank)) * kBlockM + q * 32);
               }
@@ -747,7 +757,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                              pk[4 * c + 3]);
               fence_proxy_async_smem();
               __syncwarp();
-              tma_store_5d_w(&tmap_c, buf, kx * g.cout + co0, x0, ky, y0 + 2 * q, img);
+              tma_store_5d_w(&tmap_c, buf, kx * g.cout + co0, x0, ky, y0, img);
               bulk_commit_w();
               if constexpr (Cfg::kStgBufs == 2) sbuf ^= 1;
             }
