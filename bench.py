@@ -108,7 +108,7 @@ class ClockSampler:
 
 
 class NvmlSampler:
-    """Same report as ClockSampler, sampled in-process through NVML (pynvml) from a thread every 50 ms: three light
+    """Same report as ClockSampler, sampled in-process through NVML (pynvml) from a thread every 100 ms: three light
     queries (SM clock, power, clocks-event reasons) instead of an nvidia-smi process that re-queries the device in a
     loop."""
 
@@ -144,7 +144,7 @@ class NvmlSampler:
                                   int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.1)
 
     def stop(self):
         if not self.ok:
@@ -162,7 +162,7 @@ class NvmlSampler:
         reasons = sorted(n for n, b in bits.items() if any(r[3] & b for r in rows))
         return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "sm_max_mhz": self.smax,
                 "power_w_max": max([r[2] for r in rows]) if rows else None, "samples": len(rows), "reasons": reasons,
-                "how": "in-process NVML, 50 ms"}
+                "how": "in-process NVML, 100 ms"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU / reference legs
@@ -331,20 +331,23 @@ def gpu_eager_baseline(torch, model, x, mask, obs, steps=3, warmup=2):
     return res
 
 
-def measure_config(torch, pkg, dev, encoder, size, batch, steps, warmup, peaks, model=None):
+def measure_config(torch, pkg, dev, encoder, size, batch, steps, warmup, peaks, model=None, graph=True):
     """Device-timed images/s of one more BASELINE configuration (same kernels, same timing rules)."""
     own = model is None
     if own:
         model = make_model(pkg, torch, encoder, dev)
     x, mask, obs = make_inputs(torch, batch, size, size, dev, 4321)
-    ms, out = timed_loop(torch, lambda: model(x, guide_rgb=None, guide_mask=mask, observation=obs), steps, warmup,
+    was = bool(getattr(model, "_graph", False))
+    model.set_graph(graph)
+    ms, out = timed_loop(torch, lambda: model(x, guide_rgb=None, guide_mask=mask, observation=obs), steps, max(warmup, 4),
                          torch.cuda.synchronize)
+    model.set_graph(was)
     ok = bool(torch.isfinite(out).all().item())
     rate = batch / (ms / 1e3)
     gf = GFLOP_PER_IMAGE.get((encoder, size))
     r = {"workload": f"{encoder} {size}x{size} batch {batch}", "baseline_config": BASELINE_CONFIGS.get((encoder, size, batch)),
          "value": rate, "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "finite": ok,
-         "gpu_launches_per_step": model.launch_count(),
+         "gpu_launches_per_step": model.launch_count(), "cuda_graph": bool(graph),
          "model_tflops": rate * gf / 1e3 if gf else None,
          "frac_of_sustained_peak": rate * gf / 1e3 / peaks["tf_sustained"] if gf else None,
          "frac_of_burst_peak": rate * gf / 1e3 / peaks["tf_burst"] if gf else None}
@@ -368,11 +371,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip parity / gpu_eager_baseline / other_configs / strong (profiling runs under ncu)")
-    ap.add_argument("--graph", action="store_true", help="replay the forward as a CUDA graph (launch-bound small batches)")
+    ap.add_argument("--graph", action="store_true", help="(default) replay the forward as a CUDA graph: ada_set_graph")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the ~214 kernels of a forward one by one instead (same kernels, same results; measured "
+                         "0.7 ms per step slower at batch 32 and exposed to host-side launch stalls)")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--detail", default="", help="write per-launch-signature timings of the profile pass to this JSON file")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    a.graph = not a.no_graph
     if a.impl == "reference":
         return run_reference(a)
 
