@@ -579,6 +579,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
               }
             } else {
+              // residual rows of this 64-column group: all 16-byte loads are issued before the accumulator is touched. A
+              // thread reads its own output row, so nothing coalesces and every load is a DRAM / L2 round trip; issued
+              // one pair at a time next to their use (ncu: the epilogue warps sat on long-scoreboard stalls at the first
+              // use of each loaded value) the epilogue of a 2-residual + ReLU-copy conv took longer than the K loop of the
+              // next tile: tensor pipe 54 % (877 us at 148^2 x 256 channels, batch 32) against 94 % (507 us) without residuals.
+              uint4 rz1[8], rz2[8];
+              if constexpr (EPI == EPI_BF16_RESID) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  rz1[c] = make_uint4(0u, 0u, 0u, 0u);
+                  rz2[c] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (valid) {
+                  const long long off0 = orow * g.ldo + oc;
+                  if (g.resid1) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                      if (oc + c * 8 < g.N) rz1[c] = *reinterpret_cast<const uint4*>(g.resid1 + off0 + c * 8);
+                  }
+                  if (g.resid2) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                      if (oc + c * 8 < g.N) rz2[c] = *reinterpret_cast<const uint4*>(g.resid2 + off0 + c * 8);
+                  }
+                }
+              }
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 uint32_t r[32];
@@ -615,9 +641,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     const int n = oc + h * 32 + gi * 8;
                     if (valid && n < g.N) {
-                      const long long off = orow * g.ldo + n;
-                      if (g.resid1) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid1 + off));
-                      if (g.resid2) add_bf16x8(v, *reinterpret_cast<const uint4*>(g.resid2 + off));
+                      if (g.resid1) add_bf16x8(v, rz1[h * 4 + gi]);
+                      if (g.resid2) add_bf16x8(v, rz2[h * 4 + gi]);
                     }
                   }
 #pragma unroll

@@ -42,6 +42,12 @@ tail)
   echo "=== full: tensor-core tail stand-alone"
   MODE=mma ITERS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tail_mma -s 2 -c 1 -o gpurun_out/${R}_tail_mma -f python tools/bench_tail.py > gpurun_out/${R}_tail_mma.log 2>&1; tail -1 gpurun_out/${R}_tail_mma.log | cut -c1-200
   summ tail_mma 1 ;;
+rcu)
+  echo "=== full: head 3x3 convs with residual adds (RCU conv2, EPI 8) and with a ReLU epilogue (RCU conv1, EPI 7), first forward"
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"gemm_tcgen05_kernel<.int.256, .int.2, .int.8>" -c 7 -o gpurun_out/${R}_rcu_resid -f $B > gpurun_out/${R}_rcu_resid.log 2>&1; tail -1 gpurun_out/${R}_rcu_resid.log | cut -c1-200
+  summ rcu_resid 6 7
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"gemm_tcgen05_kernel<.int.256, .int.2, .int.7>" -c 7 -o gpurun_out/${R}_rcu_relu -f $B > gpurun_out/${R}_rcu_relu.log 2>&1; tail -1 gpurun_out/${R}_rcu_relu.log | cut -c1-200
+  summ rcu_relu 7 ;;
 esac
 done
 du -sh gpurun_out
