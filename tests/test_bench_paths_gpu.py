@@ -148,3 +148,25 @@ def test_one_process_two_devices():
         outs.append(o.cpu())
     assert torch.equal(outs[0], outs[1])
     assert ((outs[1] - ref).abs() / ref).max().item() <= REL_TOL
+
+
+@pytest.mark.parametrize("enc,B,size", [("vits", 7, 266), ("vitb", 5, 154)])
+def test_pixel_tiles_spanning_images_with_a_ragged_batch(enc, B, size):
+    """The implicit-GEMM convs pick their M tile as 2^lw x 2^lh pixels of 2^lb images for least padding (csrc/ada_api.cu
+    pick_tile_geo). 266 -> maps of 76 / 38 / 19 / 10 pixels, 154 -> 44 / 22 / 11 / 6: with 7 (5) images the small maps take
+    tiles spanning 8 (4 .. 8) images, so the last tile's TMA loads zero-fill and its TMA stores clip images that do not exist.
+    Every image against the oracle, and bit-equal to one-image calls (tiles of one image, other shapes)."""
+    sd = synth.make_state_dict(enc, GT, 33)
+    inp = synth.make_inputs(B, size, size, 33)
+    m = _model(enc, GT, "invisible_part", sd)
+    out = _run(m, inp)
+    assert out.shape == (B, 1, size, size) and torch.isfinite(out).all()
+    rep = {}
+    for i in range(B):
+        ref = _oracle(sd, enc, inp, i)
+        rel, absrel = _errors(out[i:i + 1], ref, inp["mask01"][i:i + 1])
+        rep[f"img{i}"] = dict(rel=rel, absrel=absrel)
+        assert rel <= REL_TOL and absrel <= ABSREL_TOL, rep
+        one = _run(m, {k: v[i:i + 1] for k, v in inp.items()})
+        assert torch.equal(one, out[i:i + 1]), f"image {i} changes with the batch it is processed in"
+    _record(f"{enc}_{size}_b{B}_pixel_tiles", rep)
