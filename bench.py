@@ -472,9 +472,8 @@ def main():
     strong = None
     if world > 1 and a.scaling == "weak" and not a.no_extras:
         per = max(a.batch // world, 1)
-        tokens = per * ((H // 14) * (W // 14) + 1)
         sx, sm_, so = make_inputs(torch, per, H, W, dev, 99 + rank)
-        use_graph = tokens <= 12000  # launch-bound share: CUDA-graph replay (PDL is automatic below 12000 tokens)
+        use_graph = a.graph  # CUDA-graph replay like the headline loop (PDL is automatic below 12000 tokens)
         model.set_graph(use_graph)
         s_ms, s_out = timed_loop(torch, lambda: model(sx, guide_rgb=None, guide_mask=sm_, observation=so), a.steps,
                                  max(a.warmup, 4), barrier)
