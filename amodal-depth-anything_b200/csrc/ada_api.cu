@@ -747,14 +747,20 @@ static void launch_patch_gather(const float* rgb, const float* const* guides, co
   }
   src.n = n_guides + 1;
   ADA_REQUIRE(C * 196 <= Kpad, "patch gather: Kpad too small");
-  const long long total = static_cast<long long>(B) * (H / 14) * C * 14 * (W / 14);
+  ADA_REQUIRE(Kpad % 4 == 0, "patch gather: row pitch must be a multiple of 4 elements");
+  const int pw = W / 14, ph = H / 14;
+  const int chunks = (pw + kPgPatches - 1) / kPgPatches, npc = (pw + chunks - 1) / chunks;  // even split of a patch row
+  const int smem = npc * C * 196 * 2;
+  static std::atomic<uint64_t> attr_done{0};
+  ensure_smem_attr(patch_gather_kernel, kPgPatches * 8 * 196 * 2, attr_done);
+  ADA_REQUIRE(C <= 8, "patch gather: at most 8 input channels");
   ProfScope prof(PC_GATHER, 0.0, 6.0 * B * C * static_cast<double>(H) * W, st);
+  const unsigned grid = static_cast<unsigned>(B) * ph * chunks;
   if (normalize)
-    patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        src, out, B, C, H, W, Kpad, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+    patch_gather_kernel<<<grid, 256, smem, st>>>(src, out, B, C, H, W, Kpad, chunks, npc, 0.485f, 0.456f, 0.406f, 0.229f,
+                                                 0.224f, 0.225f);
   else  // un-guided model: the caller normalised the image (infer.py:18)
-    patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, out, B, C, H, W, Kpad, 0.f, 0.f,
-                                                                                     0.f, 1.f, 1.f, 1.f);
+    patch_gather_kernel<<<grid, 256, smem, st>>>(src, out, B, C, H, W, Kpad, chunks, npc, 0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
   ADA_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
 }

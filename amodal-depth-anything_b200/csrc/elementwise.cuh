@@ -207,32 +207,60 @@ struct PatchSrc {
   int ch[4];
   int n;
 };
+// One block = up to kPgPatches horizontally adjacent patches of one patch row. Phase 1 reads the C*14 image-row segments
+// they cover (each one contiguous, lanes on consecutive floats: full 128-byte requests), normalises, converts and scatters
+// into a shared-memory copy of the patches' matrix rows; phase 2 writes those rows (C*196 bf16 = 392*C bytes, contiguous in
+// the A matrix) with 8-byte stores, lanes on consecutive addresses. The first version (one thread per 14-float run, fourteen
+// 4-byte loads at a 56-byte lane stride and seven 4-byte stores into 32 different rows per instruction) ran at 1.27 TB/s.
+constexpr int kPgPatches = 32;
 __global__ void __launch_bounds__(256)
-patch_gather_kernel(PatchSrc src, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int Kpad,
+patch_gather_kernel(PatchSrc src, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int Kpad, int chunks, int npc,
                     float m0, float m1, float m2, float s0, float s1, float s2) {
+  extern __shared__ __align__(16) uint8_t pg_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(pg_smem);  // [patch][C*196]
   const int pw = W / 14, ph = H / 14;
-  const long long total = static_cast<long long>(B) * ph * C * 14 * pw;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  // idx = (((b*ph + py)*C + c)*14 + ky)*pw + px   -> consecutive threads read consecutive 56-byte runs of one image row
-  const int px = static_cast<int>(idx % pw);
-  long long t = idx / pw;
-  const int ky = static_cast<int>(t % 14); t /= 14;
-  const int c = static_cast<int>(t % C); t /= C;
-  const int py = static_cast<int>(t % ph);
-  const int b = static_cast<int>(t / ph);
-  int cs = c, si = 0;
-  while (si < src.n - 1 && cs >= src.ch[si]) { cs -= src.ch[si]; ++si; }
-  const float* p = src.ptr[si] + ((static_cast<long long>(b) * src.ch[si] + cs) * H + (py * 14 + ky)) * W + px * 14;
-  float mean = 0.f, sd = 1.f;
-  if (c == 0) { mean = m0; sd = s0; } else if (c == 1) { mean = m1; sd = s1; } else if (c == 2) { mean = m2; sd = s2; }
-  __nv_bfloat16* o = out + (static_cast<long long>(b) * ph * pw + py * pw + px) * Kpad + (c * 14 + ky) * 14;
-  uint32_t* o2 = reinterpret_cast<uint32_t*>(o);  // (c*14+ky)*14 is even -> 4-byte aligned
+  const int chunk = blockIdx.x % chunks;
+  const int py = (blockIdx.x / chunks) % ph;
+  const int b = blockIdx.x / (chunks * ph);
+  const int px0 = chunk * npc;
+  const int np = min(npc, pw - px0);  // patches of this block
+  if (np <= 0) return;
+  const int rowlen = C * 196;         // bf16 elements of one matrix row
+  const int seg = np * 14;            // floats of one image-row segment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- phase 1: (c, ky) segments round-robin over the warps
+  for (int r = warp; r < C * 14; r += 8) {
+    const int c = r / 14, ky = r % 14;
+    int cs = c, si = 0;
+    while (si < src.n - 1 && cs >= src.ch[si]) { cs -= src.ch[si]; ++si; }
+    const float* p = src.ptr[si] + ((static_cast<long long>(b) * src.ch[si] + cs) * H + (py * 14 + ky)) * W + px0 * 14;
+    float mean = 0.f, sd = 1.f;
+    if (c == 0) { mean = m0; sd = s0; } else if (c == 1) { mean = m1; sd = s1; } else if (c == 2) { mean = m2; sd = s2; }
+    __nv_bfloat16* t = tile + r * 14;
+    // all loads of the segment in flight before the first use (kPgPatches * 14 / 32 = 14 per lane): with one load per
+    // loop iteration a warp had 128 bytes in flight and the kernel was latency bound at the same 1.27 TB/s as before
+    float v[14];
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const float a = (p[2 * j] - mean) / sd;
-    const float d = (p[2 * j + 1] - mean) / sd;
-    o2[j] = pack_bf16x2(a, d);
+    for (int k = 0; k < 14; ++k) {
+      const int x = lane + 32 * k;
+      v[k] = (x < seg) ? p[x] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int x = lane + 32 * k;
+      if (x < seg) {
+        const int pl = x / 14, kx = x - pl * 14;
+        t[pl * rowlen + kx] = __float2bfloat16_rn((v[k] - mean) / sd);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: matrix rows, 8 bytes per lane (392*C bytes per row: a multiple of 8, as is the row pitch Kpad*2)
+  const int v8 = rowlen >> 2;
+  __nv_bfloat16* o = out + (static_cast<long long>(b) * ph * pw + static_cast<long long>(py) * pw + px0) * Kpad;
+  for (int i = threadIdx.x; i < np * v8; i += 256) {
+    const int pl = i / v8, k = i - pl * v8;
+    reinterpret_cast<uint2*>(o + static_cast<long long>(pl) * Kpad)[k] = reinterpret_cast<const uint2*>(tile + pl * rowlen)[k];
   }
 }
 

@@ -155,7 +155,9 @@ class NvmlSampler:
         bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
                 "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
-                "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+                "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap,
+                "hw_power_brake_slowdown": getattr(N, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+                "sync_boost": getattr(N, "nvmlClocksThrottleReasonSyncBoost", 0x10)}
         t0 = self.t_begin or 0.0
         t1 = (self.t_end or time.time()) + 0.05
         rows = [r for r in self.rows if t0 <= r[0] <= t1]
