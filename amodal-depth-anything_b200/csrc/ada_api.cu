@@ -2023,6 +2023,17 @@ int ada_interp_pos_embed_host(const float* pos_patch, int32_t grid, int32_t D, i
   });
 }
 
+int ada_conv_tile_shape(int32_t B, int32_t H, int32_t W, int32_t pair, int64_t out[4]) {
+  return guarded([&] {
+    ADA_REQUIRE(out && B > 0 && H > 0 && W > 0 && (pair == 1 || pair == 2), "bad argument");
+    const TileGeo g = pick_tile_geo(B, H, W, pair, true);
+    out[0] = g.lw;
+    out[1] = g.lh;
+    out[2] = g.lb;
+    out[3] = g.padded;
+  });
+}
+
 // ---- operator level
 int ada_op_gemm(const ada_gemm_desc* d, void* stream) {
   return guarded([&] {

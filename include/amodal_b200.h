@@ -111,6 +111,12 @@ int ada_debug_timeline(long long* out, int32_t n);
 int ada_interp_pos_embed_host(const float* pos_patch, int32_t grid, int32_t D, int32_t gh, int32_t gw, float offset,
                               float* out);
 
+/* The pixel tile an implicit-GEMM 3x3 conv launch (dpt.py:153-159,184-187,193; blocks.py:20-24,57-80) would use for an output
+ * map of B x H x W pixels: 2^lw x 2^lh pixels of 2^lb consecutive images (lw + lh + lb = 7, 2 <= 2^lw <= 32), `pair` = 1 single
+ * CTA tiles / 2 = two tiles side by side in x (cta_group::2). out = {lw, lh, lb, padded pixels incl. the padding}. The shape
+ * is picked for the fewest padded pixels; it depends on the batch, the results do not. Host only. */
+int ada_conv_tile_shape(int32_t B, int32_t H, int32_t W, int32_t pair, int64_t out[4]);
+
 /* ---- operator-level entry points (used by tests/ to check each kernel against torch on the same data) --------- */
 typedef struct ada_gemm_desc {
   const void* A;        /* bf16 [M,K] row-major (lda) or, conv mode, NHWC [B,H,W,Cin] */
@@ -134,7 +140,7 @@ typedef struct ada_gemm_desc {
   int32_t force_cg;     /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
   int32_t conv_stride;  /* conv mode: 0 / 1 = stride 1; 2 = stride 2 (resize_layers[3], dpt.py:102-107): H, W describe the
                            INPUT map, the output is ((H-1)/2+1) x ((W-1)/2+1) */
-  int32_t conv_taps;    /* conv mode: 0 / 9 = 3x3 taps; 1 = pointwise on 8x16 pixel tiles (Cin % 64 == 0) -- the k == s transposed
+  int32_t conv_taps;    /* conv mode: 0 / 9 = 3x3 taps; 1 = pointwise on 16x8 pixel tiles (Cin % 64 == 0) -- the k == s transposed
                            convs (epi 3) then store their pixel shuffle through TMA boxes (Cout % 64 == 0) */
 } ada_gemm_desc;
 int ada_op_gemm(const ada_gemm_desc* d, void* stream);

@@ -102,6 +102,39 @@ def test_pos_embed_interpolation_host_matches_reference_formula():
         assert (out - ref).abs().max().item() < 1e-4, (gh, gw)  # N(0,1) table; size= variant would differ by ~0.4
 
 
+def test_conv_pixel_tile_shapes_minimise_padding():
+    """ada_conv_tile_shape (host only): the M tile of an implicit-GEMM conv is 2^lw x 2^lh pixels x 2^lb images. For every
+    map size of the BASELINE configurations and a sweep of odd sizes / batches: 128 rows per tile, a width an epilogue
+    warp's 32 rows divide into whole tile rows, never more padded pixels than the fixed 16 x 8 x 1 tile, and the padded
+    count it reports is the one its shape implies. Known answers for the batch-32 ViT-L maps."""
+    lib = L.load()
+
+    def shape(B, H, W, pair=1):
+        out = (ctypes.c_int64 * 4)()
+        assert lib.ada_conv_tile_shape(B, H, W, pair, out) == 0
+        return tuple(int(v) for v in out)
+
+    def padded(B, H, W, pair, lw, lh, lb):
+        tw, th, nb = (1 << lw) * pair, 1 << lh, 1 << lb
+        return -(-W // tw) * tw * (-(-H // th) * th) * (-(-B // nb) * nb)
+
+    sizes = [296, 148, 74, 37, 19, 592, 10, 11, 22, 44, 5, 1, 76, 38, 49, 98, 100]
+    for B in (1, 2, 3, 4, 5, 7, 8, 32, 33):
+        for H in sizes:
+            for W in (H, max(1, H - 3), H + 12):
+                for pair in (1, 2):
+                    lw, lh, lb, pad = shape(B, H, W, pair)
+                    assert lw + lh + lb == 7 and 1 <= lw <= 5 and lh >= 0 and lb >= 0, (B, H, W, pair)
+                    assert pad == padded(B, H, W, pair, lw, lh, lb), (B, H, W, pair)
+                    assert pad <= padded(B, H, W, pair, 4, 3, 0), (B, H, W, pair)
+                    assert pad >= B * H * W
+    assert shape(32, 148, 148)[3] == 32 * 148 * 148 and shape(32, 74, 74)[3] == 32 * 74 * 74
+    assert shape(32, 296, 296)[3] == 32 * 296 * 296
+    assert shape(32, 37, 37)[3] == 32 * 38 * 38 and shape(32, 19, 19)[3] == 32 * 20 * 19
+    assert shape(1, 37, 37)[2] == 0 or shape(1, 37, 37)[3] < padded(1, 37, 37, 1, 4, 3, 0)  # one image: no batch padding wins
+    assert lib.ada_conv_tile_shape(0, 1, 1, 1, (ctypes.c_int64 * 4)()) != 0                  # ADA_EINVAL, not a crash
+
+
 def test_unguided_model_mirrors_reference_class():
     """pkg.DepthAnythingV2 = depth_anything_v2_raw/dpt.py:154-187 (the observation model of infer.py:59-61): state-dict
     template without `encoder.` prefix, guidance or input_projection; same error conventions as AmodalDAv2."""
